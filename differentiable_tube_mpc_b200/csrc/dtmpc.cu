@@ -1,0 +1,534 @@
+// dtmpc.cu -- C ABI (include/dtmpc.h) over the sm_100a kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (see __graft_entry__.build()).  No torch types cross this boundary.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "dtmpc_math.cuh"
+#include "dtmpc_sens.cuh"
+#include "dtmpc_solve.cuh"
+
+using namespace dtmpc;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return DTMPC_E_CUDA;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;  // B200
+    }
+    return cached;
+}
+
+// Python floats enter reference tensors by a plain cast to the tensor dtype; do the same here.
+template <typename R> void convert_env(const dtmpc_env &e, EnvT<R> &o) {
+    o.dt = (R)e.dt;
+    o.ndt = (R)(-e.dt);
+    o.umin0 = (R)e.u_min[0]; o.umin1 = (R)e.u_min[1];
+    o.umax0 = (R)e.u_max[0]; o.umax1 = (R)e.u_max[1];
+    o.act_lo0 = o.umin0 + (R)e.active_tol; o.act_lo1 = o.umin1 + (R)e.active_tol;
+    o.act_hi0 = o.umax0 - (R)e.active_tol; o.act_hi1 = o.umax1 - (R)e.active_tol;
+    o.nbeta = (R)(-e.obs_beta);
+    o.ninv_beta = (R)(-(1.0 / e.obs_beta));
+    o.n_obs = e.n_obs;
+    o.agg = e.obs_agg;
+    for (int i = 0; i < DTMPC_MAX_OBS; ++i) {
+        o.cx[i] = (R)e.obs_cx[i];
+        o.cy[i] = (R)e.obs_cy[i];
+        o.r2[i] = (R)(e.obs_r[i] * e.obs_r[i]);
+    }
+}
+template <typename R> void convert_ocp(const dtmpc_ocp &p, OcpT<R> &o) {
+    o.T = p.horizon;
+    o.max_iter = p.max_iter;
+    o.n_alpha = p.n_alpha;
+    o.angle_wrap = p.angle_wrap;
+    o.tight_in_jac = p.tight_in_jac;
+    o.tol = (R)p.tol;
+    o.reg = (R)p.reg;
+    for (int i = 0; i < DTMPC_MAX_ALPHAS; ++i) o.alphas[i] = (R)p.alphas[i];
+    o.eps_dyn = (R)p.eps_dyn;
+    o.eps_jac = (R)p.eps_jac;
+}
+
+bool env_ok(const dtmpc_env *e) {
+    return e && e->n_obs >= 0 && e->n_obs <= DTMPC_MAX_OBS && e->obs_agg >= 0 && e->obs_agg <= 2 && e->dt > 0.0 &&
+           (e->n_obs == 0 || e->obs_agg != DTMPC_AGG_SMOOTHMIN || e->obs_beta > 0.0);
+}
+bool ocp_ok(const dtmpc_ocp *p) {
+    return p && p->horizon >= 1 && p->max_iter >= 1 && p->n_alpha >= 1 && p->n_alpha <= DTMPC_MAX_ALPHAS;
+}
+
+template <typename R> void convert_io(const dtmpc_solve_io &s, SolveArgs<R> &a) {
+    a.x0 = (const R *)s.x0; a.V_init = (const R *)s.V_init; a.theta = (const R *)s.theta;
+    a.target = (const R *)s.target; a.Xref = (const R *)s.Xref; a.Uref = (const R *)s.Uref;
+    a.theta_stride = s.theta_stride; a.target_stride = s.target_stride;
+    a.X = (R *)s.X; a.V = (R *)s.V; a.K = (R *)s.K; a.kff = (R *)s.kff;
+    a.iters = s.iters; a.status = s.status; a.alpha_idx = s.alpha_idx;
+    a.costs = (R *)s.costs; a.margins = (R *)s.margins;
+}
+
+constexpr size_t WS_HEADER = 256;
+
+// Persistent grid: exactly the CTAs that are co-resident (a CTA that is not resident would only start
+// after the work queue has drained), i.e. SM count x occupancy of the kernel, capped by the batch.
+template <typename R> int solve_ctas_per_sm() {
+    static int cached = 0;
+    if (cached == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ilqr_kernel<R>, SOLVE_BLOCK, 0) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = 2;
+        }
+        cached = n;
+    }
+    return cached;
+}
+
+long long solve_lanes(long long B, int elem_size) {
+    long long ctas = (B + SOLVE_BLOCK - 1) / SOLVE_BLOCK;
+    const int per_sm = elem_size == 8 ? solve_ctas_per_sm<double>() : solve_ctas_per_sm<float>();
+    long long cap = (long long)sm_count() * per_sm;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    return ctas * SOLVE_BLOCK;
+}
+
+bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
+    if (!s || !s->x0 || !s->V_init || !s->theta || !s->X || !s->V) return false;
+    if (need_ref_or_target && !s->target && !(s->Xref && s->Uref)) return false;
+    if ((s->Xref == nullptr) != (s->Uref == nullptr)) return false;
+    return true;
+}
+
+template <typename R>
+int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, long long B, const dtmpc_solve_io *io0,
+               const dtmpc_solve_io *io1, void *ws, size_t ws_bytes, void *stream) {
+    const int n_stage = o1 ? 2 : 1;
+    if (!env_ok(env) || !ocp_ok(o0) || (o1 && !ocp_ok(o1))) return fail(DTMPC_E_BADARG, "bad env/ocp description");
+    if (o1 && o1->horizon != o0->horizon) return fail(DTMPC_E_BADARG, "nominal and auxiliary horizons differ");
+    if (B < 0) return fail(DTMPC_E_BADARG, "negative batch");
+    if (B == 0) return DTMPC_OK;
+    if (!io_ok(io0, true) || !io0->status) return fail(DTMPC_E_BADARG, "missing buffer in solve io");
+    if (o1 && !io_ok(io1, false)) return fail(DTMPC_E_BADARG, "missing buffer in auxiliary solve io");
+    if (!ws) return fail(DTMPC_E_BADARG, "null workspace");
+    const size_t need = dtmpc_solve_workspace_bytes(o0->horizon, B, n_stage == 2, (int)sizeof(R));
+    if (ws_bytes < need) return fail(DTMPC_E_WORKSPACE, "solve workspace too small");
+
+    SolveParams<R> P;
+    memset(&P, 0, sizeof(P));
+    convert_env(*env, P.env);
+    convert_ocp(*o0, P.ocp[0]);
+    convert_io(*io0, P.io[0]);
+    if (o1) {
+        convert_ocp(*o1, P.ocp[1]);
+        convert_io(*io1, P.io[1]);
+    }
+    P.B = B;
+    P.n_stage = n_stage;
+    P.counter = (unsigned long long *)ws;
+    P.ws = (R *)((char *)ws + WS_HEADER);
+    P.S = solve_lanes(B, (int)sizeof(R));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(ws, 0, WS_HEADER, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counter)");
+    ilqr_kernel<R><<<(unsigned)(P.S / SOLVE_BLOCK), SOLVE_BLOCK, 0, st>>>(P);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ilqr_kernel launch");
+    return DTMPC_OK;
+}
+
+template <typename R> void convert_sens(const dtmpc_sens_io &s, SensArgs<R> &a) {
+    a.X = (const R *)s.X; a.V = (const R *)s.V; a.theta = (const R *)s.theta; a.target = (const R *)s.target;
+    a.Xref = (const R *)s.Xref; a.Uref = (const R *)s.Uref; a.gx = (const R *)s.gx; a.gu = (const R *)s.gu;
+    a.Xbar = (const R *)s.Xbar;
+    a.theta_stride = s.theta_stride; a.target_stride = s.target_stride; a.xref_row = s.xref_row;
+    a.dX = (R *)s.dX; a.dV = (R *)s.dV; a.dL = (R *)s.dL; a.g_theta = (R *)s.g_theta;
+    a.gXref = (R *)s.gXref; a.gUref = (R *)s.gUref; a.loss = (R *)s.loss; a.status = s.status;
+}
+
+bool sens_io_ok(const dtmpc_sens_io *s, bool accumulate_only) {
+    if (!s || !s->X || !s->V || !s->theta || !s->dX || !s->dV || !s->dL) return false;
+    if ((s->Xref == nullptr) != (s->Uref == nullptr)) return false;
+    if (s->Xref && s->xref_row != 3 && s->xref_row != 4) return false;
+    const bool wants_cost_ref = s->g_theta || accumulate_only;
+    if (wants_cost_ref && !s->Xref && !s->target) return false;
+    if (!accumulate_only && !s->gx && !s->Xbar) return false;
+    return true;
+}
+
+template <typename R>
+int sens_impl(const dtmpc_env *env, const dtmpc_ocp *ocp, long long B, const dtmpc_sens_io *io, void *ws, size_t ws_bytes,
+              void *stream, bool accumulate_only) {
+    if (!env_ok(env) || !ocp_ok(ocp)) return fail(DTMPC_E_BADARG, "bad env/ocp description");
+    if (B < 0) return fail(DTMPC_E_BADARG, "negative batch");
+    if (B == 0) return DTMPC_OK;
+    if (!sens_io_ok(io, accumulate_only)) return fail(DTMPC_E_BADARG, "missing buffer in sensitivity io");
+    SensParams<R> P;
+    memset(&P, 0, sizeof(P));
+    convert_env(*env, P.env);
+    convert_ocp(*ocp, P.ocp);
+    convert_sens(*io, P.io);
+    P.B = B;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((B + SENS_BLOCK - 1) / SENS_BLOCK);
+    if (accumulate_only) {
+        ift_accumulate_kernel<R><<<grid, SENS_BLOCK, 0, st>>>(P);
+    } else {
+        if (!ws) return fail(DTMPC_E_BADARG, "null workspace");
+        if (ws_bytes < dtmpc_sens_workspace_bytes(ocp->horizon, B, (int)sizeof(R)))
+            return fail(DTMPC_E_WORKSPACE, "sensitivity workspace too small");
+        P.ws = (R *)ws;
+        sens_kernel<R><<<grid, SENS_BLOCK, 0, st>>>(P);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "sensitivity kernel launch");
+    return DTMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// deterministic column sums: fixed chunking (1024 rows per block) and fixed trees
+// ---------------------------------------------------------------------------
+constexpr int RED_BLOCK = 256;
+constexpr int RED_ROWS = 1024;
+
+template <typename R> __device__ __forceinline__ R block_tree_sum(R v, R *sh) {
+    // warp tree by shuffles, then a tree over the warp partials: the order depends only on the thread index
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    R t = R(0);
+    if (warp == 0) {
+        t = lane < (RED_BLOCK / 32) ? sh[lane] : R(0);
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+    }
+    return t;  // valid in thread 0
+}
+
+template <typename R>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_partial_kernel(const R *__restrict__ g, long long B, int ncols,
+                                                                   R *__restrict__ partial) {
+    __shared__ R sh[RED_BLOCK / 32];
+    const long long base = (long long)blockIdx.x * RED_ROWS;
+    for (int c = 0; c < ncols; ++c) {
+        R v = R(0);
+        for (int j = 0; j < RED_ROWS / RED_BLOCK; ++j) {
+            const long long row = base + (long long)j * RED_BLOCK + threadIdx.x;
+            if (row < B) v += g[row * ncols + c];
+        }
+        const R t = block_tree_sum(v, sh);
+        if (threadIdx.x == 0) partial[(long long)blockIdx.x * ncols + c] = t;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_final_kernel(const R *__restrict__ partial, long long nblocks,
+                                                                 int ncols, R *__restrict__ out) {
+    __shared__ R sh[RED_BLOCK / 32];
+    for (int c = 0; c < ncols; ++c) {
+        R v = R(0);
+        for (long long b = threadIdx.x; b < nblocks; b += RED_BLOCK) v += partial[b * ncols + c];
+        const R t = block_tree_sum(v, sh);
+        if (threadIdx.x == 0) out[c] = t;
+    }
+}
+
+template <typename R>
+int reduce_impl(const void *g, long long B, int ncols, void *out, void *ws, size_t ws_bytes, void *stream) {
+    if (!g || !out || ncols < 1 || B < 0) return fail(DTMPC_E_BADARG, "bad reduce arguments");
+    if (!ws || ws_bytes < dtmpc_reduce_workspace_bytes(B, ncols, (int)sizeof(R)))
+        return fail(DTMPC_E_WORKSPACE, "reduce workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nb = B > 0 ? (B + RED_ROWS - 1) / RED_ROWS : 0;
+    if (nb > 0) reduce_partial_kernel<R><<<(unsigned)nb, RED_BLOCK, 0, st>>>((const R *)g, B, ncols, (R *)ws);
+    reduce_final_kernel<R><<<1, RED_BLOCK, 0, st>>>((const R *)ws, nb, ncols, (R *)out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+    return DTMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// rollout, point-wise primitives, closed-loop plant step
+// ---------------------------------------------------------------------------
+template <typename R>
+__global__ void rollout_kernel(const __grid_constant__ EnvT<R> E, const __grid_constant__ OcpT<R> O, long long B,
+                               const R *__restrict__ x0, const R *__restrict__ V, const R *__restrict__ theta,
+                               long long theta_stride, R *__restrict__ X) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int T = O.T;
+    Theta<R> th;
+    load_theta(th, theta + i * theta_stride, O);
+    const R *xp = x0 + 4 * i;
+    State<R> x{xp[0], xp[1], xp[2], xp[3], R(0)};
+    x.Bc = barrier_of_state(E, th, x.px, x.py);
+    R *Xo = X + i * (4LL * (T + 1));
+    Xo[0] = x.px; Xo[1] = x.py; Xo[2] = x.th; Xo[3] = x.b;
+    for (int k = 0; k < T; ++k) {
+        const R u0 = V[i * (2LL * T) + 2 * k], u1 = V[i * (2LL * T) + 2 * k + 1];
+        step(E, th, x, u0, u1);
+        Xo[4 * (k + 1)] = x.px; Xo[4 * (k + 1) + 1] = x.py; Xo[4 * (k + 1) + 2] = x.th; Xo[4 * (k + 1) + 3] = x.b;
+    }
+}
+
+template <typename R>
+__global__ void primitives_kernel(const __grid_constant__ EnvT<R> E, const __grid_constant__ OcpT<R> O, long long B,
+                                  const R *__restrict__ xh, const R *__restrict__ u, const R *__restrict__ theta,
+                                  long long theta_stride, const R *__restrict__ target, R *x_next, R *A, R *Bm, R *h,
+                                  R *grad_h, R *cost, R *u_clamped, int *active, R *b0) {
+    using m = M<R>;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Theta<R> th;
+    load_theta(th, theta + i * theta_stride, O);
+    const R px = xh[4 * i], py = xh[4 * i + 1], pt = xh[4 * i + 2], pb = xh[4 * i + 3];
+    const R u0 = u[2 * i], u1 = u[2 * i + 1];
+    State<R> x{px, py, pt, pb, R(0)};
+    x.Bc = barrier_of_state(E, th, px, py);
+    step(E, th, x, u0, u1);
+    if (x_next) {
+        x_next[4 * i] = x.px; x_next[4 * i + 1] = x.py; x_next[4 * i + 2] = x.th; x_next[4 * i + 3] = x.b;
+    }
+    R hv, hx, hy;
+    eval_h<R, true>(E, px, py, hv, hx, hy);
+    if (h) h[i] = hv;
+    if (b0) b0[i] = barrier_B(hv - th.tight, th.a_jac, th.eps_jac);
+    if (grad_h) {
+        grad_h[3 * i] = hx; grad_h[3 * i + 1] = hy; grad_h[3 * i + 2] = R(0);
+    }
+    if (A || Bm) {
+        R gcx, gcy, gnx, gny, t0;
+        barrier_grad(E, th, px, py, gcx, gcy, t0);
+        barrier_grad(E, th, x.px, x.py, gnx, gny, t0);
+        Lin<R> L;
+        linearize(E, th, pt, u0, gnx, gny, gcx, gcy, L);
+        if (A) {
+            R *a = A + 16 * i;
+            a[0] = 1; a[1] = 0; a[2] = L.a02; a[3] = 0;
+            a[4] = 0; a[5] = 1; a[6] = L.a12; a[7] = 0;
+            a[8] = 0; a[9] = 0; a[10] = 1; a[11] = 0;
+            a[12] = L.r0; a[13] = L.r1; a[14] = L.r2; a[15] = th.gamma;
+        }
+        if (Bm) {
+            R *b = Bm + 8 * i;
+            b[0] = L.b00; b[1] = 0; b[2] = L.b10; b[3] = 0; b[4] = 0; b[5] = E.dt; b[6] = L.s0; b[7] = 0;
+        }
+    }
+    if (cost && target)
+        cost[i] = stage_cost(th, px, py, pt, pb, u0, u1, target[0], target[1], target[2], R(0), R(0));
+    R c0 = u0, c1 = u1;
+    clamp_u(E, c0, c1);
+    if (u_clamped) {
+        u_clamped[2 * i] = c0; u_clamped[2 * i + 1] = c1;
+    }
+    if (active) {
+        bool a0, a1;
+        active_u(E, u0, u1, a0, a1);
+        active[2 * i] = a0; active[2 * i + 1] = a1;
+    }
+    (void)m::abs_(R(0));
+}
+
+// reference core/tube_mpc.py:990-1023
+template <typename R>
+__global__ void plant_step_kernel(const __grid_constant__ EnvT<R> E, const __grid_constant__ OcpT<R> On,
+                                  const __grid_constant__ OcpT<R> Oa, long long B, const R *__restrict__ Un,
+                                  const R *__restrict__ Ua, const R *__restrict__ theta_n, long long sn,
+                                  const R *__restrict__ theta_a, long long sa, const R *__restrict__ w, R *xh, R *xhb,
+                                  R *Vn_ws, R *Va_ws) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int T = On.T;
+    Theta<R> tn, ta;
+    load_theta(tn, theta_n + i * sn, On);
+    load_theta(ta, theta_a + i * sa, Oa);
+    // the closed loop propagates b with the gradient-time DBaS config (YAML eps): tube_mpc.py:609, 614
+    tn.eps_dyn = tn.eps_jac; tn.a_dyn = tn.a_jac;
+    ta.eps_dyn = ta.eps_jac; ta.a_dyn = ta.a_jac;
+    {
+        State<R> x{xh[4 * i], xh[4 * i + 1], xh[4 * i + 2], xh[4 * i + 3], R(0)};
+        x.Bc = barrier_of_state(E, ta, x.px, x.py);
+        step(E, ta, x, Ua[i * (2LL * T)], Ua[i * (2LL * T) + 1]);
+        R w0 = R(0), w1 = R(0), w2 = R(0);
+        if (w) { w0 = w[3 * i]; w1 = w[3 * i + 1]; w2 = w[3 * i + 2]; }
+        xh[4 * i] = x.px + w0; xh[4 * i + 1] = x.py + w1; xh[4 * i + 2] = x.th + w2; xh[4 * i + 3] = x.b;
+    }
+    {
+        State<R> x{xhb[4 * i], xhb[4 * i + 1], xhb[4 * i + 2], xhb[4 * i + 3], R(0)};
+        x.Bc = barrier_of_state(E, tn, x.px, x.py);
+        step(E, tn, x, Un[i * (2LL * T)], Un[i * (2LL * T) + 1]);
+        xhb[4 * i] = x.px; xhb[4 * i + 1] = x.py; xhb[4 * i + 2] = x.th; xhb[4 * i + 3] = x.b;
+    }
+    // warm-start shift cat(U[1:], U[-1:])  (tube_mpc.py:1016-1020)
+    for (int k = 0; k < T; ++k) {
+        const int s = k + 1 < T ? k + 1 : T - 1;
+        Vn_ws[i * (2LL * T) + 2 * k] = Un[i * (2LL * T) + 2 * s];
+        Vn_ws[i * (2LL * T) + 2 * k + 1] = Un[i * (2LL * T) + 2 * s + 1];
+        Va_ws[i * (2LL * T) + 2 * k] = Ua[i * (2LL * T) + 2 * s];
+        Va_ws[i * (2LL * T) + 2 * k + 1] = Ua[i * (2LL * T) + 2 * s + 1];
+    }
+}
+
+template <typename R> __global__ void fma_peak_kernel(R *out, int iters) {
+    R a0 = R(1.0) + R(threadIdx.x) * R(1e-9), a1 = a0 + R(1), a2 = a0 + R(2), a3 = a0 + R(3);
+    R a4 = a0 + R(4), a5 = a0 + R(5), a6 = a0 + R(6), a7 = a0 + R(7);
+    const R b = R(0.999999), c = R(1e-7);
+    for (int i = 0; i < iters; ++i) {
+        a0 = M<R>::fma_(a0, b, c); a1 = M<R>::fma_(a1, b, c); a2 = M<R>::fma_(a2, b, c); a3 = M<R>::fma_(a3, b, c);
+        a4 = M<R>::fma_(a4, b, c); a5 = M<R>::fma_(a5, b, c); a6 = M<R>::fma_(a6, b, c); a7 = M<R>::fma_(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+template <typename R> double peak_impl(int iters, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int block = 256, grid = sm_count() * 8;
+    R *buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(R) * block * grid) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fma_peak_kernel<R><<<grid, block, 0, st>>>(buf, iters);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        fma_peak_kernel<R><<<grid, block, 0, st>>>(buf, iters);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * (double)iters * block * grid / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int dtmpc_abi_version(void) { return DTMPC_ABI_VERSION; }
+const char *dtmpc_last_error(void) { return g_err; }
+
+size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t tube, int32_t elem_size) {
+    (void)tube;
+    if (T < 1 || B < 0) return 0;
+    if (elem_size != 8 && elem_size != 4) return 0;
+    return WS_HEADER + (size_t)solve_ws_rows(T) * (size_t)solve_lanes(B, elem_size) * (size_t)elem_size;
+}
+size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size) {
+    if (T < 1 || B < 0) return 0;
+    return (size_t)sens_ws_rows(T) * (size_t)B * (size_t)elem_size + 256;
+}
+size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size) {
+    const long long nb = B > 0 ? (B + RED_ROWS - 1) / RED_ROWS : 0;
+    return (size_t)(nb + 1) * (size_t)ncols * (size_t)elem_size;
+}
+
+#define DTMPC_DEFINE(SUFFIX, R)                                                                                       \
+    int dtmpc_ilqr_solve_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_solve_io *io,    \
+                                  void *ws, size_t ws_bytes, void *stream) {                                          \
+        return solve_impl<R>(env, ocp, nullptr, B, io, nullptr, ws, ws_bytes, stream);                                \
+    }                                                                                                                 \
+    int dtmpc_tube_solve_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,        \
+                                  const dtmpc_solve_io *nio, const dtmpc_solve_io *aio, void *ws, size_t ws_bytes,    \
+                                  void *stream) {                                                                     \
+        if (!aux || !aio) return fail(DTMPC_E_BADARG, "tube solve needs the auxiliary OCP");                          \
+        return solve_impl<R>(env, nom, aux, B, nio, aio, ws, ws_bytes, stream);                                       \
+    }                                                                                                                 \
+    int dtmpc_sensitivity_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_sens_io *io,    \
+                                   void *ws, size_t ws_bytes, void *stream) {                                         \
+        return sens_impl<R>(env, ocp, B, io, ws, ws_bytes, stream, false);                                            \
+    }                                                                                                                 \
+    int dtmpc_ift_accumulate_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_sens_io *io, \
+                                      void *stream) {                                                                 \
+        return sens_impl<R>(env, ocp, B, io, nullptr, 0, stream, true);                                               \
+    }                                                                                                                 \
+    int dtmpc_reduce_columns_##SUFFIX(const void *g, int64_t B, int32_t ncols, void *out, void *ws, size_t ws_bytes,  \
+                                      void *stream) {                                                                 \
+        return reduce_impl<R>(g, B, ncols, out, ws, ws_bytes, stream);                                                \
+    }                                                                                                                 \
+    int dtmpc_rollout_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const void *x0, const void *V,  \
+                               const void *theta, int64_t theta_stride, void *X, void *stream) {                      \
+        if (!env_ok(env) || !ocp_ok(ocp) || B < 0) return fail(DTMPC_E_BADARG, "bad env/ocp description");            \
+        if (B == 0) return DTMPC_OK;                                                                                  \
+        if (!x0 || !V || !theta || !X) return fail(DTMPC_E_BADARG, "null buffer in rollout");                         \
+        EnvT<R> E;                                                                                                    \
+        OcpT<R> O;                                                                                                    \
+        convert_env(*env, E);                                                                                         \
+        convert_ocp(*ocp, O);                                                                                         \
+        rollout_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                             \
+            E, O, B, (const R *)x0, (const R *)V, (const R *)theta, theta_stride, (R *)X);                            \
+        cudaError_t e = cudaGetLastError();                                                                           \
+        return e == cudaSuccess ? DTMPC_OK : cuda_fail(e, "rollout kernel launch");                                   \
+    }                                                                                                                 \
+    int dtmpc_primitives_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const void *xh,              \
+                                  const void *u, const void *theta, int64_t theta_stride, const void *target,         \
+                                  void *x_next, void *A, void *Bm, void *h, void *grad_h, void *cost,                 \
+                                  void *u_clamped, int32_t *active, void *b0, void *stream) {                         \
+        if (!env_ok(env) || !ocp_ok(ocp) || B < 0) return fail(DTMPC_E_BADARG, "bad env/ocp description");            \
+        if (B == 0) return DTMPC_OK;                                                                                  \
+        if (!xh || !u || !theta) return fail(DTMPC_E_BADARG, "null buffer in primitives");                            \
+        EnvT<R> E;                                                                                                    \
+        OcpT<R> O;                                                                                                    \
+        convert_env(*env, E);                                                                                         \
+        convert_ocp(*ocp, O);                                                                                         \
+        primitives_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                          \
+            E, O, B, (const R *)xh, (const R *)u, (const R *)theta, theta_stride, (const R *)target, (R *)x_next,     \
+            (R *)A, (R *)Bm, (R *)h, (R *)grad_h, (R *)cost, (R *)u_clamped, active, (R *)b0);                       \
+        cudaError_t e = cudaGetLastError();                                                                           \
+        return e == cudaSuccess ? DTMPC_OK : cuda_fail(e, "primitives kernel launch");                                \
+    }                                                                                                                 \
+    int dtmpc_plant_step_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,        \
+                                  const void *Un, const void *Ua, const void *theta_n, int64_t sn,                    \
+                                  const void *theta_a, int64_t sa, const void *w, void *xh, void *xhb, void *Vn_ws,   \
+                                  void *Va_ws, void *stream) {                                                        \
+        if (!env_ok(env) || !ocp_ok(nom) || !ocp_ok(aux) || B < 0)                                                    \
+            return fail(DTMPC_E_BADARG, "bad env/ocp description");                                                   \
+        if (B == 0) return DTMPC_OK;                                                                                  \
+        if (!Un || !Ua || !theta_n || !theta_a || !xh || !xhb || !Vn_ws || !Va_ws)                                    \
+            return fail(DTMPC_E_BADARG, "null buffer in plant step");                                                 \
+        EnvT<R> E;                                                                                                    \
+        OcpT<R> On, Oa;                                                                                               \
+        convert_env(*env, E);                                                                                         \
+        convert_ocp(*nom, On);                                                                                        \
+        convert_ocp(*aux, Oa);                                                                                        \
+        plant_step_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                          \
+            E, On, Oa, B, (const R *)Un, (const R *)Ua, (const R *)theta_n, sn, (const R *)theta_a, sa,               \
+            (const R *)w, (R *)xh, (R *)xhb, (R *)Vn_ws, (R *)Va_ws);                                                 \
+        cudaError_t e = cudaGetLastError();                                                                           \
+        return e == cudaSuccess ? DTMPC_OK : cuda_fail(e, "plant step kernel launch");                                \
+    }
+
+DTMPC_DEFINE(f64, double)
+DTMPC_DEFINE(f32, float)
+
+double dtmpc_measure_fp64_peak_tflops(int32_t iters, void *stream) { return peak_impl<double>(iters, stream); }
+double dtmpc_measure_fp32_peak_tflops(int32_t iters, void *stream) { return peak_impl<float>(iters, stream); }
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+// dtmpc_math.cuh -- device primitives of the Dubins + DBaS problem family.
+//
+// Compiled with -fmad=false: every fused multiply-add below is written
+// explicitly (fma_), so a formula produces the same bits wherever it is
+// inlined (rollout, line-search candidates, winner recomputation, jacobian).
+// The line search relies on that: the alpha = 0 candidate is the current
+// trajectory bit for bit and is never re-evaluated.
+//
+// Reference formulas (file:line relative to the reference root) are cited per
+// function; evaluation order follows them except where a dense product with
+// structural zeros/ones is written out sparsely (adding exact zeros).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/dtmpc.h"
+
+namespace dtmpc {
+
+template <typename R> struct M;  // math dispatch
+template <> struct M<double> {
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ double exp_(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return ::log(x); }
+    static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double max_(double a, double b) { return ::fmax(a, b); }
+    static __device__ __forceinline__ double min_(double a, double b) { return ::fmin(a, b); }
+    static __device__ __forceinline__ double abs_(double a) { return ::fabs(a); }
+    static __device__ __forceinline__ double inf_() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double nan_() { return __longlong_as_double(0x7ff8000000000000LL); }
+};
+template <> struct M<float> {
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
+    static __device__ __forceinline__ float exp_(float x) { return ::expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return ::logf(x); }
+    static __device__ __forceinline__ void sincos_(float x, float *s, float *c) { ::sincosf(x, s, c); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return ::atan2f(y, x); }
+    static __device__ __forceinline__ float max_(float a, float b) { return ::fmaxf(a, b); }
+    static __device__ __forceinline__ float min_(float a, float b) { return ::fminf(a, b); }
+    static __device__ __forceinline__ float abs_(float a) { return ::fabsf(a); }
+    static __device__ __forceinline__ float inf_() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float nan_() { return __int_as_float(0x7fc00000); }
+};
+
+template <typename R> __device__ __forceinline__ bool finite_(R v) { return M<R>::abs_(v) < M<R>::inf_(); }
+
+// ---------------------------------------------------------------------------
+// Kernel-parameter copies of the POD specs, converted to the arithmetic type
+// on the host exactly as the reference converts Python floats to tensors.
+// ---------------------------------------------------------------------------
+template <typename R> struct EnvT {
+    R dt, ndt;                  // dt and -dt
+    R umin0, umin1, umax0, umax1;
+    R act_lo0, act_lo1, act_hi0, act_hi1;  // u_min + tol, u_max - tol (core/control.py:70)
+    R nbeta, ninv_beta;         // -beta, -(1/beta)
+    int n_obs, agg;
+    R cx[DTMPC_MAX_OBS], cy[DTMPC_MAX_OBS], r2[DTMPC_MAX_OBS];
+};
+
+template <typename R> struct OcpT {
+    int T, max_iter, n_alpha, angle_wrap, tight_in_jac;
+    R tol, reg;
+    R alphas[DTMPC_MAX_ALPHAS];
+    R eps_dyn, eps_jac;
+};
+
+// Per-instance constrained parameters + derived barrier constants.
+template <typename R> struct Theta {
+    R Q0, Q1, Q2, R0, R1, Qf0, Qf1, Qf2, qb, alpha, gamma, tight;
+    // a = max(alpha, eps) for the dynamics (eps_dyn) and for the jacobian/gradients (eps_jac)
+    R a_dyn, a_jac, jac_off;
+    // per-OCP numerical settings, kept with the lane so that lanes of one warp may work on
+    // different OCPs (nominal / auxiliary) without divergent constant-bank reads
+    R eps_dyn, eps_jac;
+    int angle_wrap;
+};
+
+template <typename R>
+__device__ __forceinline__ void load_theta(Theta<R> &t, const R *__restrict__ p, const OcpT<R> &o) {
+    t.Q0 = p[0]; t.Q1 = p[1]; t.Q2 = p[2];
+    t.R0 = p[3]; t.R1 = p[4];
+    t.Qf0 = p[5]; t.Qf1 = p[6]; t.Qf2 = p[7];
+    t.qb = p[8]; t.alpha = p[9]; t.gamma = p[10]; t.tight = p[11];
+    t.eps_dyn = o.eps_dyn;
+    t.eps_jac = o.eps_jac;
+    t.angle_wrap = o.angle_wrap;
+    t.a_dyn = M<R>::max_(t.alpha, o.eps_dyn);  // core/barrier.py:49
+    t.a_jac = M<R>::max_(t.alpha, o.eps_jac);
+    t.jac_off = o.tight_in_jac ? t.tight : R(0);
+}
+
+// ---------------------------------------------------------------------------
+// Safety function h and its gradient.
+//   h_i = dx*dx + dy*dy - r^2                      core/systems/dubins_obstacles.py:27-30
+//   smooth-min: z = -beta*h_i, lse = zmax + log(sum exp(z - zmax)), h = -(1/beta)*lse   :63-69
+//   grad: softmax(z) weighted sum of 2(p - c_i)      :84-92   (normalised once by the sum)
+//   min: min_i h_i, gradient of the first argmin     :104-106, 115-117
+//   single circle: h_0, 2(p - c_0)                   :16-38
+//   empty list: h = 1, grad = 0                      :57-61, 81-82
+// ---------------------------------------------------------------------------
+template <typename R, bool GRAD>
+__device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx, R &gy) {
+    using m = M<R>;
+    const int n = e.n_obs;
+    gx = R(0);
+    gy = R(0);
+    if (n == 0) {
+        h = R(1);
+        return;
+    }
+    if (e.agg == DTMPC_AGG_SINGLE) {
+        R dx = px - e.cx[0], dy = py - e.cy[0];
+        h = m::fma_(dy, dy, dx * dx) - e.r2[0];
+        if (GRAD) {
+            gx = R(2) * dx;
+            gy = R(2) * dy;
+        }
+        return;
+    }
+    if (e.agg == DTMPC_AGG_MIN) {
+        R best = m::inf_();
+        R bx = R(0), by = R(0);
+        for (int i = 0; i < n; ++i) {
+            R dx = px - e.cx[i], dy = py - e.cy[i];
+            R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+            if (hi < best || i == 0) {
+                best = hi;
+                bx = dx;
+                by = dy;
+            }
+        }
+        h = best;
+        if (GRAD) {
+            gx = R(2) * bx;
+            gy = R(2) * by;
+        }
+        return;
+    }
+    R zmax = -m::inf_();
+    for (int i = 0; i < n; ++i) {
+        R dx = px - e.cx[i], dy = py - e.cy[i];
+        R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+        zmax = m::max_(zmax, e.nbeta * hi);
+    }
+    R s = R(0), sx = R(0), sy = R(0);
+    for (int i = 0; i < n; ++i) {
+        R dx = px - e.cx[i], dy = py - e.cy[i];
+        R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+        R w = m::exp_(e.nbeta * hi - zmax);
+        s += w;
+        if (GRAD) {
+            sx = m::fma_(w, R(2) * dx, sx);
+            sy = m::fma_(w, R(2) * dy, sy);
+        }
+    }
+    h = e.ninv_beta * (zmax + m::log_(s));
+    if (GRAD) {
+        gx = sx / s;
+        gy = sy / s;
+    }
+}
+
+// Relaxed inverse barrier, core/barrier.py:36-59, with a = max(alpha, eps) precomputed.
+template <typename R> __device__ __forceinline__ R barrier_B(R z, R a, R eps) {
+    if (z >= a) return R(1) / M<R>::max_(z, eps);
+    R d = z - a;
+    return (R(1) / a) - d / (a * a) + (d * d) / (a * a * a);
+}
+
+// d B / d zeta, core/systems/dubins_aug_jac.py:26-40
+template <typename R> __device__ __forceinline__ R barrier_dB(R z, R a, R eps) {
+    if (z >= a) {
+        R zc = M<R>::max_(z, eps);
+        return R(-1) / (zc * zc);
+    }
+    R d = z - a;
+    return -(R(1) / (a * a)) + (R(2) * d) / (a * a * a);
+}
+
+// d B / d a in the relaxed branch (0 in the safe branch); differentiates core/barrier.py:56-58.
+template <typename R> __device__ __forceinline__ R barrier_dB_da(R z, R a) {
+    if (z >= a) return R(0);
+    R d = z - a;
+    R a2 = a * a;
+    return R(-3) * d * d / (a2 * a2);
+}
+
+// core/control.py:61-64
+template <typename R> __device__ __forceinline__ void clamp_u(const EnvT<R> &e, R &u0, R &u1) {
+    u0 = M<R>::min_(M<R>::max_(u0, e.umin0), e.umax0);
+    u1 = M<R>::min_(M<R>::max_(u1, e.umin1), e.umax1);
+}
+
+// core/control.py:66-70
+template <typename R> __device__ __forceinline__ void active_u(const EnvT<R> &e, R u0, R u1, bool &a0, bool &a1) {
+    a0 = (u0 <= e.act_lo0) || (u0 >= e.act_hi0);
+    a1 = (u1 <= e.act_lo1) || (u1 >= e.act_hi1);
+}
+
+// run_nominal.py:32-34
+template <typename R> __device__ __forceinline__ R wrap_angle(R err) {
+    R s, c;
+    M<R>::sincos_(err, &s, &c);
+    return M<R>::atan2_(s, c);
+}
+
+// Augmented state carried along a rollout: (px, py, th, b) plus B(h_bar(x)) of the
+// CURRENT state, which the next DBaS step needs as B_curr (core/barrier.py:94-98);
+// h(x_{k+1}) of step k is h(x_k) of step k+1, so it is evaluated once.
+template <typename R> struct State {
+    R px, py, th, b, Bc;
+};
+
+// B_curr for a state that did not come out of step() (the initial state).
+template <typename R>
+__device__ __forceinline__ R barrier_of_state(const EnvT<R> &e, const Theta<R> &t, R px, R py) {
+    R h, gx, gy;
+    eval_h<R, false>(e, px, py, h, gx, gy);
+    return barrier_B(h - t.tight, t.a_dyn, t.eps_dyn);
+}
+
+// One step of f_hat: dubins_step (core/systems/dubins.py:36-42) + dbas_step (core/barrier.py:93-108).
+template <typename R>
+__device__ __forceinline__ void step(const EnvT<R> &e, const Theta<R> &t, State<R> &x, R u0, R u1) {
+    using m = M<R>;
+    R s, c;
+    m::sincos_(x.th, &s, &c);
+    R dtv = e.dt * u0;
+    R pxn = m::fma_(dtv, c, x.px);
+    R pyn = m::fma_(dtv, s, x.py);
+    R thn = m::fma_(e.dt, u1, x.th);
+    R h, gx, gy;
+    eval_h<R, false>(e, pxn, pyn, h, gx, gy);
+    R Bn = barrier_B(h - t.tight, t.a_dyn, t.eps_dyn);
+    // b+ = B_next - gamma * (B_curr - b)
+    R bn = m::fma_(-t.gamma, x.Bc - x.b, Bn);
+    x.px = pxn;
+    x.py = pyn;
+    x.th = thn;
+    x.b = bn;
+    x.Bc = Bn;
+}
+
+// Stage cost  sum Q dx^2 + sum R du^2 + q_b b^2   (core/tube_mpc.py:823-827, 875-880; 281-286, 358-364)
+template <typename R>
+__device__ __forceinline__ R stage_cost(const Theta<R> &t, R px, R py, R th, R b, R u0, R u1, R xr0, R xr1, R xr2,
+                                        R ur0, R ur1) {
+    using m = M<R>;
+    R d0 = px - xr0, d1 = py - xr1, d2 = th - xr2;
+    if (t.angle_wrap) d2 = wrap_angle(d2);
+    R e0 = u0 - ur0, e1 = u1 - ur1;
+    R sx = (t.Q0 * d0) * d0;
+    sx = m::fma_(t.Q1 * d1, d1, sx);
+    sx = m::fma_(t.Q2 * d2, d2, sx);
+    R su = (t.R0 * e0) * e0;
+    su = m::fma_(t.R1 * e1, e1, su);
+    return m::fma_(t.qb, b * b, sx + su);
+}
+
+// Terminal cost  sum Qf dx^2 + q_b b^2   (core/tube_mpc.py:829-832, 882-885; 288-293, 366-371)
+template <typename R>
+__device__ __forceinline__ R terminal_cost(const Theta<R> &t, R px, R py, R th, R b, R xr0, R xr1, R xr2) {
+    using m = M<R>;
+    R d0 = px - xr0, d1 = py - xr1, d2 = th - xr2;
+    if (t.angle_wrap) d2 = wrap_angle(d2);
+    R sx = (t.Qf0 * d0) * d0;
+    sx = m::fma_(t.Qf1 * d1, d1, sx);
+    sx = m::fma_(t.Qf2 * d2, d2, sx);
+    return m::fma_(t.qb, b * b, sx);
+}
+
+// Heading error used by the cost DERIVATIVES: x - target with the target shifted so that the
+// error is the wrapped one (run_nominal.py:311-315); plain difference otherwise.
+template <typename R> __device__ __forceinline__ R heading_err_for_derivs(const Theta<R> &t, R th, R xr2) {
+    if (!t.angle_wrap) return th - xr2;
+    R tk = th - wrap_angle(th - xr2);
+    return th - tk;
+}
+
+// g(x) = B'(h_jac(x)) * grad h(x): the barrier row of the augmented jacobian is built from g at
+// x_k and x_{k+1} (core/systems/dubins_aug_jac.py:95-129).  Also returns h(x) (unshifted).
+template <typename R>
+__device__ __forceinline__ void barrier_grad(const EnvT<R> &e, const Theta<R> &t, R px, R py, R &gx, R &gy, R &h) {
+    R hx, hy;
+    eval_h<R, true>(e, px, py, h, hx, hy);
+    R dB = barrier_dB(h - t.jac_off, t.a_jac, t.eps_jac);
+    gx = dB * hx;
+    gy = dB * hy;
+}
+
+// Non-trivial entries of A = d f_hat / d x_hat (4x4) and B = d f_hat / d u (4x2):
+//   A = [1 0 a02 0; 0 1 a12 0; 0 0 1 0; r0 r1 r2 gamma],  B = [b00 0; b10 0; 0 dt; s0 0]
+// (core/systems/dubins_aug_jac.py:43-58, 128-138; B[3,1] = g_theta * dt = 0 because h has no heading term).
+template <typename R> struct Lin {
+    R a02, a12, r0, r1, r2, b00, b10, s0;
+};
+
+template <typename R>
+__device__ __forceinline__ void linearize(const EnvT<R> &e, const Theta<R> &t, R th, R v, R gnx, R gny, R gcx, R gcy,
+                                          Lin<R> &L) {
+    using m = M<R>;
+    R s, c;
+    m::sincos_(th, &s, &c);
+    L.a02 = (e.ndt * v) * s;
+    L.a12 = (e.dt * v) * c;
+    L.b00 = e.dt * c;
+    L.b10 = e.dt * s;
+    L.r0 = m::fma_(-t.gamma, gcx, gnx);
+    L.r1 = m::fma_(-t.gamma, gcy, gny);
+    L.r2 = m::fma_(gny, L.a12, gnx * L.a02);
+    L.s0 = m::fma_(gny, L.b10, gnx * L.b00);
+}
+
+// 2x2 solve with partial pivoting (what torch.linalg.solve / LAPACK getrf+getrs does, core/ddp.py:243-244):
+// factor once, then solve_rhs per right-hand side.
+template <typename R> struct LU2 {
+    R a00, a01, l, u11;
+    bool swap;
+};
+template <typename R> __device__ __forceinline__ void lu2_factor(LU2<R> &f, R q00, R q01, R q10, R q11) {
+    f.swap = M<R>::abs_(q10) > M<R>::abs_(q00);
+    R r00 = f.swap ? q10 : q00, r01 = f.swap ? q11 : q01;
+    R r10 = f.swap ? q00 : q10, r11 = f.swap ? q01 : q11;
+    f.a00 = r00;
+    f.a01 = r01;
+    f.l = r10 / r00;
+    f.u11 = M<R>::fma_(-f.l, r01, r11);
+}
+template <typename R> __device__ __forceinline__ void lu2_solve(const LU2<R> &f, R b0, R b1, R &x0, R &x1) {
+    R c0 = f.swap ? b1 : b0, c1 = f.swap ? b0 : b1;
+    R y1 = M<R>::fma_(-f.l, c0, c1);
+    x1 = y1 / f.u11;
+    x0 = M<R>::fma_(-f.a01, x1, c0) / f.a00;
+}
+
+}  // namespace dtmpc

@@ -1,0 +1,137 @@
+"""Batched two-layer tube MPC: one call = what one closed-loop step of the reference computes per instance.
+
+  nominal ilqr_solve -> auxiliary ilqr_solve -> upper loss -> ddp_sensitivity(aux) -> theta gradient
+  [-> ddp_sensitivity(nominal) driven by dL/dx_ref, dL/du_ref -> theta_bar gradient]   (full mode)
+
+reference: core/tube_mpc.py:844-976 (paper mode) and :305-602 (full mode).  The batch is sharded across
+ranks (one process per GPU); the only collective is the all-reduce of the batch-summed gradient when the
+parameters are shared (Algorithm 2), see `allreduce_shared`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .spec import TubeProblem
+
+
+@dataclass
+class TubeStep:
+    nominal: ops.SolveResult
+    auxiliary: ops.SolveResult
+    sens_aux: ops.SensitivityResult
+    sens_nom: Optional[ops.SensitivityResult]
+    loss: Tensor                 # [B] upper loss per instance (core/tube_mpc.py:916-919)
+    g_aux_sum: Tensor            # [13] = batch sums of d/d(constrained theta) [12] and of the loss [1]
+    g_nom_sum: Optional[Tensor]  # [12] batch sums of d/d(constrained theta_bar) (full mode)
+
+    @property
+    def status(self) -> Tensor:
+        return self.nominal.status
+
+
+class BatchedTubeMPC:
+    """Solver for B independent tube-MPC instances on one GPU."""
+
+    def __init__(self, problem: TubeProblem, device="cuda", dtype=torch.float64, gains: bool = False,
+                 trace: bool = False):
+        self.problem = problem
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("BatchedTubeMPC runs on a CUDA device only (no CPU fallback)")
+        self.dtype = dtype
+        self.gains = gains
+        self.trace = trace
+        self.workspace = ops.Workspace(self.device)
+        self.timers: Optional[Dict[str, list]] = None   # filled with CUDA events when enabled (bench.py)
+        self.launches = 0                                # kernels of this library launched so far
+
+    # -- initial barrier state b0 = B(h(x0) - tight)  (core/barrier.py:111-120) -------------
+    def init_barrier(self, x: Tensor, theta: Tensor, nominal: bool) -> Tensor:
+        ocp = self.problem.nominal if nominal else self.problem.auxiliary
+        B = x.shape[0]
+        xh = torch.cat([x, torch.zeros(B, 1, dtype=x.dtype, device=x.device)], dim=1)
+        u = torch.zeros(B, 2, dtype=x.dtype, device=x.device)
+        self.launches += 1
+        return ops.primitives_batched(self.problem.system, ocp, xh, u, theta)["b0"]
+
+    def _timed(self, name):
+        eng = self
+
+        class _T:
+            def __enter__(self_inner):
+                if eng.timers is not None:
+                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e0.record()
+                return self_inner
+
+            def __exit__(self_inner, *exc):
+                if eng.timers is not None:
+                    self_inner.e1.record()
+                    eng.timers.setdefault(name, []).append((self_inner.e0, self_inner.e1))
+                return False
+
+        return _T()
+
+    def step(self, x0_nom: Tensor, x0_aux: Tensor, Vn_init: Tensor, Va_init: Tensor, theta_nom: Tensor,
+             theta_aux: Tensor, target: Optional[Tensor] = None, full: Optional[bool] = None) -> TubeStep:
+        """All tensors on self.device: x0_* [B,4], V*_init [B,T,2], theta_* [12] or [B,12] (constrained values)."""
+        p = self.problem
+        full = (p.mode == "full") if full is None else full
+        with self._timed("tube_solve"):
+            rn, ra = ops.tube_solve_batched(p.system, p.nominal, p.auxiliary, x0_nom, x0_aux, Vn_init, Va_init,
+                                            theta_nom, theta_aux, target=target, gains=self.gains, trace=self.trace,
+                                            workspace=self.workspace)
+        self.launches += 1
+        with self._timed("sens_aux"):
+            sa = ops.ddp_sensitivity_batched(p.system, p.auxiliary, ra.X, ra.V, theta_aux, X_bar=rn.X, X_ref=rn.X,
+                                             U_ref=rn.V, want_grads=True, want_ref_grads=full, status=rn.status,
+                                             workspace=self.workspace)
+        self.launches += 1
+        sn = None
+        g_nom_sum = None
+        if full:
+            B, T = rn.X.shape[0], rn.V.shape[1]
+            # upper gradients of the nominal problem: [dL/dx_ref, 0] and dL/du_ref (core/tube_mpc.py:520-535)
+            gx = torch.cat([sa.g_xref, torch.zeros(B, T + 1, 1, dtype=self.dtype, device=self.device)], dim=2)
+            with self._timed("sens_nom"):
+                sn = ops.ddp_sensitivity_batched(p.system, p.nominal, rn.X, rn.V, theta_nom, upper_grad_x=gx,
+                                                 upper_grad_u=sa.g_uref, target=target, want_grads=True,
+                                                 status=rn.status, workspace=self.workspace)
+            self.launches += 1
+        with self._timed("reduce"):
+            g_aux_sum = ops.reduce_columns(torch.cat([sa.g_theta, sa.loss.view(-1, 1)], dim=1), self.workspace)
+            self.launches += 2
+            if full:
+                g_nom_sum = ops.reduce_columns(sn.g_theta, self.workspace)
+                self.launches += 2
+        return TubeStep(nominal=rn, auxiliary=ra, sens_aux=sa, sens_nom=sn, loss=sa.loss, g_aux_sum=g_aux_sum,
+                        g_nom_sum=g_nom_sum)
+
+
+def allreduce_shared(step: TubeStep, group=None) -> TubeStep:
+    """Sum the batch-summed gradients (and the loss) over the data-parallel ranks: the one collective of the path
+    (Algorithm 2 with shared theta; < 200 bytes, latency bound).  No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return step
+    if step.g_nom_sum is not None:
+        buf = torch.cat([step.g_aux_sum, step.g_nom_sum])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        step.g_aux_sum, step.g_nom_sum = buf[:13].clone(), buf[13:].clone()
+    else:
+        dist.all_reduce(step.g_aux_sum, op=dist.ReduceOp.SUM, group=group)
+    return step
+
+
+def shard_bounds(total: int, world_size: int, rank: int):
+    """Contiguous slice [lo, hi) of a batch of `total` instances owned by `rank`."""
+    base, rem = divmod(int(total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

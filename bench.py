@@ -286,8 +286,13 @@ def main():
             ms = float(t.item())
         return ms, last
 
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: at least W (>= 3) steps AND ~2 s of load -- the first launches pay lazy module loading and the SM
+    # clocks need a few hundred ms to ramp from idle (first two steps measured 2-9x slower than steady state)
+    n_warm, t_warm = 0, time.perf_counter()
+    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_warm) < 2.0:
         device_step()
+        torch.cuda.synchronize()
+        n_warm += 1
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -335,7 +340,7 @@ def main():
                             "sample": f"{n} instances of the same seeded workload, {cores} threads, C port of the "
                                       "reference algorithm (oracle/dtmpc_oracle.c)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "warmup": n_warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

@@ -87,30 +87,37 @@ template <typename R> void convert_io(const dtmpc_solve_io &s, SolveArgs<R> &a) 
     a.costs = (R *)s.costs; a.margins = (R *)s.margins;
 }
 
-constexpr size_t WS_HEADER = 256;
+// ---------------------------------------------------------------------------
+// iLQR solver: workspace carving and the per-iteration launch sequence
+// ---------------------------------------------------------------------------
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// Persistent grid: exactly the CTAs that are co-resident (a CTA that is not resident would only start
-// after the work queue has drained), i.e. SM count x occupancy of the kernel, capped by the batch.
-template <typename R> int solve_ctas_per_sm() {
-    static int cached = 0;
-    if (cached == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ilqr_kernel<R>, SOLVE_BLOCK, 0) != cudaSuccess || n < 1) {
-            (void)cudaGetLastError();
-            n = 2;
-        }
-        cached = n;
+// Carves the caller's scratch into the solver arrays; with base == nullptr only the size is computed.
+template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int n_alpha, SolveWs<R> *w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base ? base + off : nullptr;
+        off = align_up(off + bytes);
+        return p;
+    };
+    const size_t nB = (size_t)B;
+    char *counts = take(256);
+    char *l0 = take(nB * sizeof(int)), *l1 = take(nB * sizeof(int));
+    char *cur = take(nB * sizeof(int)), *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
+    char *Jcur = take(nB * sizeof(R)), *prev = take(nB * sizeof(R)), *B0 = take(nB * sizeof(R));
+    char *J = take(nB * sizeof(R) * (size_t)n_alpha);
+    char *traj = take(nB * sizeof(R) * (size_t)traj_rows(T) * (size_t)(n_alpha + 1));
+    char *gains = take(nB * sizeof(R) * 10 * (size_t)T);
+    char *lin = take(nB * sizeof(R) * 8 * (size_t)T);
+    char *ref = take(nB * sizeof(R) * (size_t)ref_rows(T));
+    if (w) {
+        w->counts = (int *)counts;
+        w->list[0] = (int *)l0; w->list[1] = (int *)l1;
+        w->cur = (int *)cur; w->it = (int *)it; w->flags = (int *)flags;
+        w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0; w->J = (R *)J;
+        w->traj = (R *)traj; w->gains = (R *)gains; w->lin = (R *)lin; w->ref = (R *)ref;
     }
-    return cached;
-}
-
-long long solve_lanes(long long B, int elem_size) {
-    long long ctas = (B + SOLVE_BLOCK - 1) / SOLVE_BLOCK;
-    const int per_sm = elem_size == 8 ? solve_ctas_per_sm<double>() : solve_ctas_per_sm<float>();
-    long long cap = (long long)sm_count() * per_sm;
-    if (ctas > cap) ctas = cap;
-    if (ctas < 1) ctas = 1;
-    return ctas * SOLVE_BLOCK;
+    return off;
 }
 
 bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
@@ -120,41 +127,71 @@ bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
     return true;
 }
 
+// One batched OCP: init, max_iter x (linearise, Riccati, line search, select), write-out.  Everything is
+// stream-ordered; the host never waits, so all max_iter iterations are enqueued and the ones that find the
+// active list empty return at once.
+template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
+    const long long B = P.B;
+    const int T = P.ocp.T;
+    const unsigned gB = (unsigned)((B + LS_BLOCK - 1) / LS_BLOCK);
+    P.n_eval = 0;
+    for (int c = 0; c < P.ocp.n_alpha; ++c)
+        if (P.ocp.alphas[c] != R(0)) P.eval_idx[P.n_eval++] = c;
+    P.parity = 0;
+    init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+    const unsigned gLin = (unsigned)((B * T + 255) / 256);
+    const unsigned gFwd = (unsigned)((B + 31) / 32);
+    for (int it = 0; it < P.ocp.max_iter; ++it) {
+        lin_kernel<R><<<gLin, 256, 0, st>>>(P);
+        ric_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+        if (P.n_eval > 0) fwd_kernel<R><<<gFwd, dim3(32, P.n_eval), 0, st>>>(P);
+        sel_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+        P.parity ^= 1;
+    }
+    out_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "iLQR kernel launch");
+    return DTMPC_OK;
+}
+
 template <typename R>
 int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, long long B, const dtmpc_solve_io *io0,
                const dtmpc_solve_io *io1, void *ws, size_t ws_bytes, void *stream) {
-    const int n_stage = o1 ? 2 : 1;
     if (!env_ok(env) || !ocp_ok(o0) || (o1 && !ocp_ok(o1))) return fail(DTMPC_E_BADARG, "bad env/ocp description");
     if (o1 && o1->horizon != o0->horizon) return fail(DTMPC_E_BADARG, "nominal and auxiliary horizons differ");
-    if (B < 0) return fail(DTMPC_E_BADARG, "negative batch");
+    if (B < 0 || B > 0x7fffffffLL) return fail(DTMPC_E_BADARG, "batch size out of range");
     if (B == 0) return DTMPC_OK;
     if (!io_ok(io0, true) || !io0->status) return fail(DTMPC_E_BADARG, "missing buffer in solve io");
     if (o1 && !io_ok(io1, false)) return fail(DTMPC_E_BADARG, "missing buffer in auxiliary solve io");
     if (!ws) return fail(DTMPC_E_BADARG, "null workspace");
-    const size_t need = dtmpc_solve_workspace_bytes(o0->horizon, B, n_stage == 2, (int)sizeof(R));
-    if (ws_bytes < need) return fail(DTMPC_E_WORKSPACE, "solve workspace too small");
+    const int n_alpha = o1 && o1->n_alpha > o0->n_alpha ? o1->n_alpha : o0->n_alpha;
+    if (ws_bytes < dtmpc_solve_workspace_bytes(o0->horizon, B, n_alpha, (int)sizeof(R)))
+        return fail(DTMPC_E_WORKSPACE, "solve workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
 
     SolveParams<R> P;
     memset(&P, 0, sizeof(P));
     convert_env(*env, P.env);
-    convert_ocp(*o0, P.ocp[0]);
-    convert_io(*io0, P.io[0]);
-    if (o1) {
-        convert_ocp(*o1, P.ocp[1]);
-        convert_io(*io1, P.io[1]);
-    }
+    convert_ocp(*o0, P.ocp);
+    convert_io(*io0, P.io);
+    carve_solve_ws<R>((char *)ws, o0->horizon, B, n_alpha, &P.ws);
     P.B = B;
-    P.n_stage = n_stage;
-    P.counter = (unsigned long long *)ws;
-    P.ws = (R *)((char *)ws + WS_HEADER);
-    P.S = solve_lanes(B, (int)sizeof(R));
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(ws, 0, WS_HEADER, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counter)");
-    ilqr_kernel<R><<<(unsigned)(P.S / SOLVE_BLOCK), SOLVE_BLOCK, 0, st>>>(P);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "ilqr_kernel launch");
-    return DTMPC_OK;
+    P.use_ref = io0->Xref != nullptr;
+    P.ref_from_io = P.use_ref;
+    P.write_ref = o1 != nullptr;
+    P.status_shift = 0;
+    int rc = launch_ocp(P, st);
+    if (rc != DTMPC_OK || !o1) return rc;
+
+    // auxiliary OCP tracking the nominal solution that out_kernel left in ws.ref (core/tube_mpc.py:864-865)
+    convert_ocp(*o1, P.ocp);
+    convert_io(*io1, P.io);
+    P.io.status = io0->status;
+    P.use_ref = 1;
+    P.ref_from_io = 0;
+    P.write_ref = 0;
+    P.status_shift = 4;
+    return launch_ocp(P, st);
 }
 
 template <typename R> void convert_sens(const dtmpc_sens_io &s, SensArgs<R> &a) {
@@ -435,11 +472,11 @@ extern "C" {
 int dtmpc_abi_version(void) { return DTMPC_ABI_VERSION; }
 const char *dtmpc_last_error(void) { return g_err; }
 
-size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t tube, int32_t elem_size) {
-    (void)tube;
-    if (T < 1 || B < 0) return 0;
-    if (elem_size != 8 && elem_size != 4) return 0;
-    return WS_HEADER + (size_t)solve_ws_rows(T) * (size_t)solve_lanes(B, elem_size) * (size_t)elem_size;
+size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size) {
+    if (T < 1 || B < 0 || n_alpha < 1 || n_alpha > DTMPC_MAX_ALPHAS) return 0;
+    if (elem_size == 8) return carve_solve_ws<double>(nullptr, T, B, n_alpha, nullptr);
+    if (elem_size == 4) return carve_solve_ws<float>(nullptr, T, B, n_alpha, nullptr);
+    return 0;
 }
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size) {
     if (T < 1 || B < 0) return 0;

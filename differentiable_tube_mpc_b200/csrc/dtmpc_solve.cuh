@@ -1,20 +1,25 @@
-// dtmpc_solve.cuh -- persistent batched iLQR kernel (reference core/ddp.py:102-307).
+// dtmpc_solve.cuh -- batched iLQR (reference core/ddp.py:102-307) as phase-synchronous kernels.
 //
-// Mapping: one problem per thread.  The sweep is serial in T and the blocks are
-// tiny (nx = 4, nu = 2), so the Riccati blocks live in registers and all
-// parallelism is across the batch.  Iteration counts differ per instance
-// (reference: 2..20), so lanes are persistent workers: when a lane's OCP
-// converges it writes its result and pulls the next instance from a global
-// counter.  A warp therefore always executes the same phase (rollout /
-// backward / line search / commit) with lanes at different iterations -- and,
-// for the two-layer solve, in different OCPs (nominal vs auxiliary), which is
-// the same code with different per-lane parameters.
+// The sweep is serial in T and the blocks are tiny (nx = 4, nu = 2): all parallelism is across the batch, and the
+// kernel is FP64-pipe bound, not HBM bound.  Every iLQR iteration of the whole batch is four launches over the list
+// of still-active instances:
 //
-// Working set per lane (trajectory X,V; gains K,k; tracked reference) lives in
-// a slot-major structure-of-arrays scratch:  row r of lane s at ws[r*S + s],
-// so every per-timestep access of a warp is one contiguous 256 B segment.
-// Results leave the kernel instance-major ([B,T+1,4] ...): one state is one
-// 32 B sector, which keeps scattered writes from refilled lanes sector-exact.
+//   lin_kernel   thread per (instance, k)          linearisation: sincos, h, grad h, B' -> 8 jacobian entries
+//                                                  (embarrassingly parallel in k: taken off the serial chain)
+//   ric_kernel   thread per instance               backward Riccati sweep, register-resident V_x / V_xx, gains K, k
+//   fwd_kernel   thread per (instance, candidate)  forward line search: every alpha != 0 rolls out in its own lane,
+//                                                  one warp per candidate, 32 instances per CTA, so the gains and the
+//                                                  current trajectory are fetched once per CTA (L1) for all candidates
+//   sel_kernel   thread per instance               argmin (strict <, first wins), tolerance break, trace, compaction
+//                                                  of the active list
+//
+// Candidates write their trajectories into per-candidate buffers; accepting a step is an index update (`cur`), nothing
+// is recomputed or copied.  The alpha = 0 candidate is the current trajectory bit for bit (dtmpc_math.cuh) and costs
+// nothing.  Instances that have converged leave the active list, so warps stay full while iteration counts differ
+// (reference: 2..20 iterations per instance).
+//
+// Scratch is instance-minor structure-of-arrays (row r of instance i at base[r*B + i]): every access of a warp is a
+// contiguous segment.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
 #pragma once
 #include "dtmpc_math.cuh"
 
@@ -28,433 +33,482 @@ template <typename R> struct SolveArgs {
     R *costs, *margins;
 };
 
+template <typename R> struct SolveWs {
+    int *counts;     // [2] sizes of the two active lists
+    int *list[2];    // active instance indices (double buffered)
+    int *cur;        // [B] buffer holding the current trajectory
+    int *it;         // [B] completed iterations
+    int *flags;      // [B] bit 0: non-finite in the backward pass
+    R *Jcur, *prev, *B0;  // [B] cost of the current trajectory, previous accepted cost, B(h(x0) - tight)
+    R *J;            // [n_alpha][B] candidate costs
+    R *traj;         // [n_buf][4(T+1)+2T][B]
+    R *gains;        // [10T][B]  K (8 rows per k) then k (2 rows per k)
+    R *lin;          // [8T][B]
+    R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)
+};
+
 template <typename R> struct SolveParams {
     EnvT<R> env;
-    OcpT<R> ocp[2];
-    SolveArgs<R> io[2];
+    OcpT<R> ocp;
+    SolveArgs<R> io;
+    SolveWs<R> ws;
     long long B;
-    int n_stage;  // 1: single OCP, 2: nominal then auxiliary tracking the nominal result
-    unsigned long long *counter;
-    R *ws;
-    long long S;  // number of lanes (scratch stride)
+    int n_eval;                      // candidates that are actually rolled out (alpha != 0)
+    int eval_idx[DTMPC_MAX_ALPHAS];  // their positions in the alpha list
+    int use_ref;                     // 1: track ws.ref, 0: track io.target
+    int ref_from_io;                 // 1: init copies io.Xref / io.Uref into ws.ref
+    int write_ref;                   // 1: out_kernel also writes ws.ref (nominal solution -> auxiliary reference)
+    int status_shift;                // 0 (single / nominal) or 4 (auxiliary)
+    int parity;                      // active list read by this launch
 };
 
-constexpr int SOLVE_BLOCK = 128;
+constexpr int LS_BLOCK = 128;
 
-// scratch rows per lane
-__host__ __device__ inline long long solve_ws_rows(int T) {
-    return 4LL * (T + 1) + 2LL * T + 8LL * T + 2LL * T + 3LL * (T + 1) + 2LL * T;
-}
+__host__ __device__ inline long long traj_rows(int T) { return 4LL * (T + 1) + 2LL * T; }
+__host__ __device__ inline long long ref_rows(int T) { return 3LL * (T + 1) + 2LL * T; }
 
-template <typename R> struct Cand {
-    State<R> x;
-    R J;
-};
+template <typename R> struct RefPt { R x0, x1, x2, u0, u1; };
 
 template <typename R>
-__global__ void __launch_bounds__(SOLVE_BLOCK) ilqr_kernel(const __grid_constant__ SolveParams<R> P) {
-    using m = M<R>;
+__device__ __forceinline__ void ref_at(const SolveParams<R> &P, long long i, int k, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
+    if (P.use_ref) {
+        const long long S = P.B;
+        const int T = P.ocp.T;
+        r.x0 = P.ws.ref[(3LL * k + 0) * S + i];
+        r.x1 = P.ws.ref[(3LL * k + 1) * S + i];
+        r.x2 = P.ws.ref[(3LL * k + 2) * S + i];
+        if (with_u) {
+            r.u0 = P.ws.ref[(3LL * (T + 1) + 2LL * k + 0) * S + i];
+            r.u1 = P.ws.ref[(3LL * (T + 1) + 2LL * k + 1) * S + i];
+        } else {
+            r.u0 = R(0); r.u1 = R(0);
+        }
+    } else {
+        r.x0 = t0; r.x1 = t1; r.x2 = t2; r.u0 = R(0); r.u1 = R(0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// init: V = clamp(V_init), X = rollout(x0, V)  (core/ddp.py:125-131); every instance enters the active list
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(const __grid_constant__ SolveParams<R> P) {
+    const long long i = (long long)blockIdx.x * LS_BLOCK + threadIdx.x;
+    if (i == 0) {
+        P.ws.counts[0] = (int)P.B;
+        P.ws.counts[1] = 0;
+    }
+    if (i >= P.B) return;
     const EnvT<R> &E = P.env;
-    const long long S = P.S;
-    const long long slot = (long long)blockIdx.x * SOLVE_BLOCK + threadIdx.x;
-    const int T = P.ocp[0].T;
-    R *const wX = P.ws + slot;
-    R *const wV = wX + 4LL * (T + 1) * S;
-    R *const wK = wV + 2LL * T * S;
-    R *const wk = wK + 8LL * T * S;
-    R *const wXr = wk + 2LL * T * S;
-    R *const wUr = wXr + 3LL * (T + 1) * S;
-    const unsigned FULL = 0xffffffffu;
-
-    // ---- per-lane solver state -------------------------------------------
-    long long inst = -1;  // -1: needs work, -2: queue exhausted
-    int stage = 0, it = 0, status = 0;
-    bool fresh = false, have_prev = false, use_ref = false;
-    R prev = R(0), Jcur = R(0), B0 = R(0);
-    R x00 = R(0), x01 = R(0), x02 = R(0), x03 = R(0);
-    R tg0 = R(0), tg1 = R(0), tg2 = R(0);
-    R tol = R(0), reg = R(0);
-    int max_iter = 0, n_alpha = 0;
+    const int T = P.ocp.T;
+    const long long S = P.B;
     Theta<R> th;
+    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+    if (P.ref_from_io) {
+        const R *xr = P.io.Xref + i * (3LL * (T + 1));
+        const R *ur = P.io.Uref + i * (2LL * T);
+        for (int r = 0; r < 3 * (T + 1); ++r) P.ws.ref[(long long)r * S + i] = xr[r];
+        for (int r = 0; r < 2 * T; ++r) P.ws.ref[(3LL * (T + 1) + r) * S + i] = ur[r];
+    }
+    R t0 = R(0), t1 = R(0), t2 = R(0);
+    if (!P.use_ref) {
+        const R *tp = P.io.target + i * P.io.target_stride;
+        t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
+    }
+    const R *x0p = P.io.x0 + i * 4;
+    State<R> x{x0p[0], x0p[1], x0p[2], x0p[3], R(0)};
+    x.Bc = barrier_of_state(E, th, x.px, x.py);
+    P.ws.B0[i] = x.Bc;
+    R *X = P.ws.traj + i;                       // buffer 0
+    R *V = X + 4LL * (T + 1) * S;
+    X[0 * S] = x.px; X[1 * S] = x.py; X[2 * S] = x.th; X[3 * S] = x.b;
+    const R *vp = P.io.V_init + i * (2LL * T);
+    R J = R(0);
+    for (int k = 0; k < T; ++k) {
+        R u0 = vp[2 * k], u1 = vp[2 * k + 1];
+        clamp_u(E, u0, u1);
+        V[(2LL * k) * S] = u0;
+        V[(2LL * k + 1) * S] = u1;
+        RefPt<R> r;
+        ref_at(P, i, k, true, t0, t1, t2, r);
+        J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
+        step(E, th, x, u0, u1);
+        X[(4LL * (k + 1) + 0) * S] = x.px;
+        X[(4LL * (k + 1) + 1) * S] = x.py;
+        X[(4LL * (k + 1) + 2) * S] = x.th;
+        X[(4LL * (k + 1) + 3) * S] = x.b;
+    }
+    RefPt<R> r;
+    ref_at(P, i, T, false, t0, t1, t2, r);
+    J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
+    P.ws.Jcur[i] = J;
+    P.ws.prev[i] = R(0);
+    P.ws.cur[i] = 0;
+    P.ws.it[i] = 0;
+    P.ws.flags[i] = 0;
+    P.ws.list[0][i] = (int)i;
+    if (P.status_shift == 0) P.io.status[i] = 0;
+}
 
-#define WS(base, row) (base)[(long long)(row) * S]
-#define REF_AT(k, r0, r1, r2)                  \
-    do {                                       \
-        if (use_ref) {                         \
-            r0 = WS(wXr, 3 * (k) + 0);         \
-            r1 = WS(wXr, 3 * (k) + 1);         \
-            r2 = WS(wXr, 3 * (k) + 2);         \
-        } else {                               \
-            r0 = tg0; r1 = tg1; r2 = tg2;      \
-        }                                      \
-    } while (0)
-#define UREF_AT(k, q0, q1)                     \
-    do {                                       \
-        if (use_ref) {                         \
-            q0 = WS(wUr, 2 * (k) + 0);         \
-            q1 = WS(wUr, 2 * (k) + 1);         \
-        } else {                               \
-            q0 = R(0); q1 = R(0);              \
-        }                                      \
-    } while (0)
+// ---------------------------------------------------------------------------------------------------------------
+// linearisation (core/ddp.py:172-199 -> core/systems/dubins_aug_jac.py:61-139), thread per (instance, k)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(256) lin_kernel(const __grid_constant__ SolveParams<R> P) {
+    const int n_act = P.ws.counts[P.parity];
+    const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (g == 0) P.ws.counts[P.parity ^ 1] = 0;  // the list sel_kernel will fill
+    const int T = P.ocp.T;
+    if (g >= (long long)n_act * T) return;
+    const int j = (int)(g % n_act), k = (int)(g / n_act);
+    const long long i = P.ws.list[P.parity][j];
+    const long long S = P.B;
+    const EnvT<R> &E = P.env;
+    Theta<R> th;
+    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+    const R *X = P.ws.traj + (long long)P.ws.cur[i] * traj_rows(T) * S + i;
+    const R *V = X + 4LL * (T + 1) * S;
+    const R pth = X[(4LL * k + 2) * S];
+    const R v = V[(2LL * k) * S];
+    R gnx, gny, gcx = R(0), gcy = R(0), hv;
+    barrier_grad(E, th, X[(4LL * (k + 1) + 0) * S], X[(4LL * (k + 1) + 1) * S], gnx, gny, hv);
+    if (th.gamma != R(0)) barrier_grad(E, th, X[(4LL * k + 0) * S], X[(4LL * k + 1) * S], gcx, gcy, hv);
+    Lin<R> L;
+    linearize(E, th, pth, v, gnx, gny, gcx, gcy, L);
+    R *o = P.ws.lin + (8LL * k) * S + i;
+    o[0 * S] = L.a02; o[1 * S] = L.a12; o[2 * S] = L.r0; o[3 * S] = L.r1;
+    o[4 * S] = L.r2; o[5 * S] = L.b00; o[6 * S] = L.b10; o[7 * S] = L.s0;
+}
 
-    // Loads everything a lane needs to start OCP `stage` of instance `inst`
-    // (reference core/ddp.py:125-129: V = clamp(V_init)).
-    auto setup_stage = [&]() {
-        const OcpT<R> &o = P.ocp[stage];
-        const SolveArgs<R> &a = P.io[stage];
-        load_theta(th, a.theta + inst * a.theta_stride, o);
-        tol = o.tol;
-        reg = o.reg;
-        max_iter = o.max_iter;
-        n_alpha = o.n_alpha;
-        const R *x0p = a.x0 + inst * 4;
-        x00 = x0p[0]; x01 = x0p[1]; x02 = x0p[2]; x03 = x0p[3];
-        B0 = barrier_of_state(E, th, x00, x01);
-        const R *vp = a.V_init + inst * (2LL * T);
-        for (int k = 0; k < T; ++k) {
-            R u0 = vp[2 * k], u1 = vp[2 * k + 1];
-            clamp_u(E, u0, u1);
-            WS(wV, 2 * k) = u0;
-            WS(wV, 2 * k + 1) = u1;
-        }
-        if (stage == 1 && P.n_stage == 2) {
-            use_ref = true;  // reference already staged by finish_stage()
-        } else if (a.Xref != nullptr) {
-            use_ref = true;
-            const R *xr = a.Xref + inst * (3LL * (T + 1));
-            const R *ur = a.Uref + inst * (2LL * T);
-            for (int k = 0; k <= T; ++k) {
-                WS(wXr, 3 * k + 0) = xr[3 * k + 0];
-                WS(wXr, 3 * k + 1) = xr[3 * k + 1];
-                WS(wXr, 3 * k + 2) = xr[3 * k + 2];
-            }
-            for (int k = 0; k < T; ++k) {
-                WS(wUr, 2 * k + 0) = ur[2 * k + 0];
-                WS(wUr, 2 * k + 1) = ur[2 * k + 1];
-            }
-        } else {
-            use_ref = false;
-            const R *tp = a.target + inst * a.target_stride;
-            tg0 = tp[0]; tg1 = tp[1]; tg2 = tp[2];
-        }
-        it = 0;
-        have_prev = false;
-        fresh = true;
+// ---------------------------------------------------------------------------------------------------------------
+// backward Riccati sweep (core/ddp.py:208-254), thread per instance
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(const __grid_constant__ SolveParams<R> P) {
+    using m = M<R>;
+    const int n_act = P.ws.counts[P.parity];
+    const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
+    if (j >= n_act) return;
+    const long long i = P.ws.list[P.parity][j];
+    const long long S = P.B;
+    const EnvT<R> &E = P.env;
+    const int T = P.ocp.T;
+    Theta<R> th;
+    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+    R t0 = R(0), t1 = R(0), t2 = R(0);
+    if (!P.use_ref) {
+        const R *tp = P.io.target + i * P.io.target_stride;
+        t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
+    }
+    const R *X = P.ws.traj + (long long)P.ws.cur[i] * traj_rows(T) * S + i;
+    const R *V = X + 4LL * (T + 1) * S;
+    const R *LN = P.ws.lin + i;
+    R *GK = P.ws.gains + i;
+    R *Gk = GK + 8LL * T * S;
+    const R reg = P.ocp.reg;
+
+    R Vx0, Vx1, Vx2, Vx3;
+    R V00, V01, V02, V03, V10, V11, V12, V13, V20, V21, V22, V23, V30, V31, V32, V33;
+    {
+        const R px = X[(4LL * T + 0) * S], py = X[(4LL * T + 1) * S], pt = X[(4LL * T + 2) * S], pb = X[(4LL * T + 3) * S];
+        RefPt<R> r;
+        ref_at(P, i, T, false, t0, t1, t2, r);
+        // terminal derivatives: core/cost_derivs.py:132-146 + barrier entries core/tube_mpc.py:839-841
+        Vx0 = (R(2) * th.Qf0) * (px - r.x0);
+        Vx1 = (R(2) * th.Qf1) * (py - r.x1);
+        Vx2 = (R(2) * th.Qf2) * heading_err_for_derivs(th, pt, r.x2);
+        Vx3 = (R(2) * th.qb) * pb;
+        V00 = R(2) * th.Qf0; V11 = R(2) * th.Qf1; V22 = R(2) * th.Qf2; V33 = R(2) * th.qb;
+        V01 = V02 = V03 = V10 = V12 = V13 = V20 = V21 = V23 = V30 = V31 = V32 = R(0);
+    }
+    const R lxx0 = R(2) * th.Q0, lxx1 = R(2) * th.Q1, lxx2 = R(2) * th.Q2, lxx3 = R(2) * th.qb;
+    const R luu0 = R(2) * th.R0, luu1 = R(2) * th.R1;
+    const R gam = th.gamma, dt = E.dt;
+    bool bad = false;
+    // inputs of step k are fetched one step ahead of their use (see fwd_kernel)
+    struct RicIn {
+        R px, py, pt, pb, u0, u1;
+        RefPt<R> r;
+        Lin<R> L;
     };
-
-    // Writes the lane's result instance-major and either chains into the auxiliary OCP or frees the lane.
-    auto finish_stage = [&](int st_bits) {
-        const SolveArgs<R> &a = P.io[stage];
-        R *Xo = a.X + inst * (4LL * (T + 1));
-        R *Vo = a.V + inst * (2LL * T);
-        for (int k = 0; k <= T; ++k) {
-            Xo[4 * k + 0] = WS(wX, 4 * k + 0);
-            Xo[4 * k + 1] = WS(wX, 4 * k + 1);
-            Xo[4 * k + 2] = WS(wX, 4 * k + 2);
-            Xo[4 * k + 3] = WS(wX, 4 * k + 3);
-        }
-        for (int k = 0; k < T; ++k) {
-            Vo[2 * k + 0] = WS(wV, 2 * k + 0);
-            Vo[2 * k + 1] = WS(wV, 2 * k + 1);
-        }
-        if (a.K != nullptr) {
-            R *Ko = a.K + inst * (8LL * T);
-            for (int r = 0; r < 8 * T; ++r) Ko[r] = WS(wK, r);
-        }
-        if (a.kff != nullptr) {
-            R *ko = a.kff + inst * (2LL * T);
-            for (int r = 0; r < 2 * T; ++r) ko[r] = WS(wk, r);
-        }
-        if (a.iters != nullptr) a.iters[inst] = it;
-        status |= st_bits << (4 * stage);
-        if (P.n_stage == 2 && stage == 0 && st_bits == 0) {
-            // the nominal solution becomes the tracked reference (core/tube_mpc.py:864-865)
-            for (int k = 0; k <= T; ++k) {
-                WS(wXr, 3 * k + 0) = WS(wX, 4 * k + 0);
-                WS(wXr, 3 * k + 1) = WS(wX, 4 * k + 1);
-                WS(wXr, 3 * k + 2) = WS(wX, 4 * k + 2);
-            }
-            for (int r = 0; r < 2 * T; ++r) WS(wUr, r) = WS(wV, r);
-            stage = 1;
-            setup_stage();
-        } else {
-            P.io[0].status[inst] = status;
-            inst = -1;
-        }
+    auto load_step = [&](int k, RicIn &q) {
+        q.px = X[(4LL * k + 0) * S]; q.py = X[(4LL * k + 1) * S]; q.pt = X[(4LL * k + 2) * S]; q.pb = X[(4LL * k + 3) * S];
+        q.u0 = V[(2LL * k) * S]; q.u1 = V[(2LL * k + 1) * S];
+        ref_at(P, i, k, true, t0, t1, t2, q.r);
+        const R *o = LN + (8LL * k) * S;
+        q.L.a02 = o[0 * S]; q.L.a12 = o[1 * S]; q.L.r0 = o[2 * S]; q.L.r1 = o[3 * S];
+        q.L.r2 = o[4 * S]; q.L.b00 = o[5 * S]; q.L.b10 = o[6 * S]; q.L.s0 = o[7 * S];
     };
+    RicIn in;
+    load_step(T - 1, in);
+    for (int k = T - 1; k >= 0; --k) {
+        RicIn nx;
+        load_step(k > 0 ? k - 1 : 0, nx);
+        const R px = in.px, py = in.py, pt = in.pt, pb = in.pb, u0 = in.u0, u1 = in.u1;
+        const RefPt<R> r = in.r;
+        const Lin<R> L = in.L;
+        in = nx;
+        // stage derivatives, core/cost_derivs.py:58-76, 110-129
+        const R lx0 = lxx0 * (px - r.x0), lx1 = lxx1 * (py - r.x1);
+        const R lx2 = lxx2 * heading_err_for_derivs(th, pt, r.x2), lx3 = lxx3 * pb;
+        const R lu0 = luu0 * (u0 - r.u0), lu1 = luu1 * (u1 - r.u1);
 
-    for (;;) {
-        // ---- work acquisition --------------------------------------------
-        if (inst == -1) {
-            unsigned long long t = atomicAdd(P.counter, 1ULL);
-            if (t >= (unsigned long long)P.B) {
-                inst = -2;
-            } else {
-                inst = (long long)t;
-                stage = 0;
-                status = 0;
-                setup_stage();
-            }
-        }
-        if (__all_sync(FULL, inst == -2)) break;
-        const bool live = inst >= 0;
-
-        // ---- phase R: initial rollout of freshly loaded OCPs (core/ddp.py:131) ----
-        if (__any_sync(FULL, live && fresh)) {
-            if (live && fresh) {
-                State<R> x{x00, x01, x02, x03, B0};
-                R J = R(0);
-                WS(wX, 0) = x00; WS(wX, 1) = x01; WS(wX, 2) = x02; WS(wX, 3) = x03;
-                for (int k = 0; k < T; ++k) {
-                    R u0 = WS(wV, 2 * k), u1 = WS(wV, 2 * k + 1);
-                    R r0, r1, r2, q0, q1;
-                    REF_AT(k, r0, r1, r2);
-                    UREF_AT(k, q0, q1);
-                    J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r0, r1, r2, q0, q1);
-                    step(E, th, x, u0, u1);
-                    WS(wX, 4 * (k + 1) + 0) = x.px;
-                    WS(wX, 4 * (k + 1) + 1) = x.py;
-                    WS(wX, 4 * (k + 1) + 2) = x.th;
-                    WS(wX, 4 * (k + 1) + 3) = x.b;
-                }
-                R r0, r1, r2;
-                REF_AT(T, r0, r1, r2);
-                J += terminal_cost(th, x.px, x.py, x.th, x.b, r0, r1, r2);
-                Jcur = J;
-                fresh = false;
-            }
-        }
-
-        bool bad = false;
-        if (live) {
-            // ---- phase B: linearise + backward Riccati sweep (core/ddp.py:172-254) ----
-            R Vx0, Vx1, Vx2, Vx3;
-            R V00, V01, V02, V03, V10, V11, V12, V13, V20, V21, V22, V23, V30, V31, V32, V33;
-            R gnx, gny;
-            {
-                R px = WS(wX, 4 * T + 0), py = WS(wX, 4 * T + 1), pt = WS(wX, 4 * T + 2), pb = WS(wX, 4 * T + 3);
-                R r0, r1, r2;
-                REF_AT(T, r0, r1, r2);
-                // terminal derivatives: core/cost_derivs.py:132-146 + barrier entries core/tube_mpc.py:839-841
-                Vx0 = (R(2) * th.Qf0) * (px - r0);
-                Vx1 = (R(2) * th.Qf1) * (py - r1);
-                Vx2 = (R(2) * th.Qf2) * heading_err_for_derivs(th, pt, r2);
-                Vx3 = (R(2) * th.qb) * pb;
-                V00 = R(2) * th.Qf0; V11 = R(2) * th.Qf1; V22 = R(2) * th.Qf2; V33 = R(2) * th.qb;
-                V01 = V02 = V03 = V10 = V12 = V13 = V20 = V21 = V23 = V30 = V31 = V32 = R(0);
-                R hT;
-                barrier_grad(E, th, px, py, gnx, gny, hT);
-            }
-            const R lxx0 = R(2) * th.Q0, lxx1 = R(2) * th.Q1, lxx2 = R(2) * th.Q2, lxx3 = R(2) * th.qb;
-            const R luu0 = R(2) * th.R0, luu1 = R(2) * th.R1;
-            const R gam = th.gamma, dt = E.dt;
-            for (int k = T - 1; k >= 0; --k) {
-                const R px = WS(wX, 4 * k + 0), py = WS(wX, 4 * k + 1), pt = WS(wX, 4 * k + 2), pb = WS(wX, 4 * k + 3);
-                const R u0 = WS(wV, 2 * k), u1 = WS(wV, 2 * k + 1);
-                R r0, r1, r2, q0, q1;
-                REF_AT(k, r0, r1, r2);
-                UREF_AT(k, q0, q1);
-                R gcx, gcy, hk;
-                barrier_grad(E, th, px, py, gcx, gcy, hk);
-                Lin<R> L;
-                linearize(E, th, pt, u0, gnx, gny, gcx, gcy, L);
-                gnx = gcx;
-                gny = gcy;
-                // stage derivatives, core/cost_derivs.py:58-76, 110-129
-                const R lx0 = lxx0 * (px - r0), lx1 = lxx1 * (py - r1);
-                const R lx2 = lxx2 * heading_err_for_derivs(th, pt, r2), lx3 = lxx3 * pb;
-                const R lu0 = luu0 * (u0 - q0), lu1 = luu1 * (u1 - q1);
-
-                // M = V_xx A   (A = [1 0 a02 0; 0 1 a12 0; 0 0 1 0; r0 r1 r2 gamma])
+        // M = V_xx A   (A = [1 0 a02 0; 0 1 a12 0; 0 0 1 0; r0 r1 r2 gamma])
 #define ROW_M(i)                                                                              \
     const R M##i##0 = m::fma_(V##i##3, L.r0, V##i##0);                                        \
     const R M##i##1 = m::fma_(V##i##3, L.r1, V##i##1);                                        \
     const R M##i##2 = m::fma_(V##i##3, L.r2, m::fma_(V##i##1, L.a12, m::fma_(V##i##0, L.a02, V##i##2))); \
     const R M##i##3 = V##i##3 * gam;
-                ROW_M(0) ROW_M(1) ROW_M(2) ROW_M(3)
+        ROW_M(0) ROW_M(1) ROW_M(2) ROW_M(3)
 #undef ROW_M
-                // Q_xx = l_xx + A^T M
+        // Q_xx = l_xx + A^T M
 #define COL_Q(j)                                                                              \
     R Qxx0##j = m::fma_(L.r0, M3##j, M0##j);                                                  \
     R Qxx1##j = m::fma_(L.r1, M3##j, M1##j);                                                  \
     R Qxx2##j = m::fma_(L.r2, M3##j, m::fma_(L.a12, M1##j, m::fma_(L.a02, M0##j, M2##j)));    \
     R Qxx3##j = gam * M3##j;
-                COL_Q(0) COL_Q(1) COL_Q(2) COL_Q(3)
+        COL_Q(0) COL_Q(1) COL_Q(2) COL_Q(3)
 #undef COL_Q
-                Qxx00 += lxx0; Qxx11 += lxx1; Qxx22 += lxx2; Qxx33 += lxx3;
-                // Q_ux = B^T M   (B = [b00 0; b10 0; 0 dt; s0 0])
+        Qxx00 += lxx0; Qxx11 += lxx1; Qxx22 += lxx2; Qxx33 += lxx3;
+        // Q_ux = B^T M   (B = [b00 0; b10 0; 0 dt; s0 0])
 #define COL_U(j)                                                                              \
     const R Qux0##j = m::fma_(L.s0, M3##j, m::fma_(L.b10, M1##j, L.b00 * M0##j));             \
     const R Qux1##j = dt * M2##j;
-                COL_U(0) COL_U(1) COL_U(2) COL_U(3)
+        COL_U(0) COL_U(1) COL_U(2) COL_U(3)
 #undef COL_U
-                // V_xx B columns, Q_uu = l_uu + B^T V_xx B
-                const R w0 = m::fma_(V03, L.s0, m::fma_(V01, L.b10, V00 * L.b00));
-                const R w1 = m::fma_(V13, L.s0, m::fma_(V11, L.b10, V10 * L.b00));
-                const R w2 = m::fma_(V23, L.s0, m::fma_(V21, L.b10, V20 * L.b00));
-                const R w3 = m::fma_(V33, L.s0, m::fma_(V31, L.b10, V30 * L.b00));
-                const R y0 = V02 * dt, y1 = V12 * dt, y2 = V22 * dt, y3 = V32 * dt;
-                const R Quu00 = luu0 + m::fma_(L.s0, w3, m::fma_(L.b10, w1, L.b00 * w0));
-                const R Quu01 = m::fma_(L.s0, y3, m::fma_(L.b10, y1, L.b00 * y0));
-                const R Quu10 = dt * w2;
-                const R Quu11 = luu1 + dt * y2;
-                // Q_x = l_x + A^T V_x, Q_u = l_u + B^T V_x
-                const R Qx0 = lx0 + m::fma_(L.r0, Vx3, Vx0);
-                const R Qx1 = lx1 + m::fma_(L.r1, Vx3, Vx1);
-                const R Qx2 = lx2 + m::fma_(L.r2, Vx3, m::fma_(L.a12, Vx1, m::fma_(L.a02, Vx0, Vx2)));
-                const R Qx3 = lx3 + gam * Vx3;
-                const R Qu0 = lu0 + m::fma_(L.s0, Vx3, m::fma_(L.b10, Vx1, L.b00 * Vx0));
-                const R Qu1 = lu1 + dt * Vx2;
-                // gains: K = -(Q_uu + reg I)^-1 Q_ux, k = -(Q_uu + reg I)^-1 Q_u   (core/ddp.py:239-244)
-                LU2<R> F;
-                lu2_factor(F, Quu00 + reg, Quu01, Quu10, Quu11 + reg);
-                R K00, K01, K02, K03, K10, K11, K12, K13, k0, k1;
-                lu2_solve(F, Qux00, Qux10, K00, K10);
-                lu2_solve(F, Qux01, Qux11, K01, K11);
-                lu2_solve(F, Qux02, Qux12, K02, K12);
-                lu2_solve(F, Qux03, Qux13, K03, K13);
-                lu2_solve(F, Qu0, Qu1, k0, k1);
-                K00 = -K00; K01 = -K01; K02 = -K02; K03 = -K03;
-                K10 = -K10; K11 = -K11; K12 = -K12; K13 = -K13;
-                k0 = -k0; k1 = -k1;
-                WS(wK, 8 * k + 0) = K00; WS(wK, 8 * k + 1) = K01; WS(wK, 8 * k + 2) = K02; WS(wK, 8 * k + 3) = K03;
-                WS(wK, 8 * k + 4) = K10; WS(wK, 8 * k + 5) = K11; WS(wK, 8 * k + 6) = K12; WS(wK, 8 * k + 7) = K13;
-                WS(wk, 2 * k + 0) = k0; WS(wk, 2 * k + 1) = k1;
-                // V_x = Q_x + K^T Q_uu k + K^T Q_u + Q_xu k   (un-regularised Q_uu, core/ddp.py:251)
-                const R t0 = m::fma_(Quu01, k1, Quu00 * k0) + Qu0;
-                const R t1 = m::fma_(Quu11, k1, Quu10 * k0) + Qu1;
-                Vx0 = Qx0 + m::fma_(K10, t1, K00 * t0) + m::fma_(Qux10, k1, Qux00 * k0);
-                Vx1 = Qx1 + m::fma_(K11, t1, K01 * t0) + m::fma_(Qux11, k1, Qux01 * k0);
-                Vx2 = Qx2 + m::fma_(K12, t1, K02 * t0) + m::fma_(Qux12, k1, Qux02 * k0);
-                Vx3 = Qx3 + m::fma_(K13, t1, K03 * t0) + m::fma_(Qux13, k1, Qux03 * k0);
-                // V_xx = Q_xx + K^T Q_uu K + K^T Q_ux + Q_xu K   (never symmetrised, core/ddp.py:252)
+        // V_xx B columns, Q_uu = l_uu + B^T V_xx B
+        const R w0 = m::fma_(V03, L.s0, m::fma_(V01, L.b10, V00 * L.b00));
+        const R w1 = m::fma_(V13, L.s0, m::fma_(V11, L.b10, V10 * L.b00));
+        const R w2 = m::fma_(V23, L.s0, m::fma_(V21, L.b10, V20 * L.b00));
+        const R w3 = m::fma_(V33, L.s0, m::fma_(V31, L.b10, V30 * L.b00));
+        const R y0 = V02 * dt, y1 = V12 * dt, y2 = V22 * dt, y3 = V32 * dt;
+        const R Quu00 = luu0 + m::fma_(L.s0, w3, m::fma_(L.b10, w1, L.b00 * w0));
+        const R Quu01 = m::fma_(L.s0, y3, m::fma_(L.b10, y1, L.b00 * y0));
+        const R Quu10 = dt * w2;
+        const R Quu11 = luu1 + dt * y2;
+        // Q_x = l_x + A^T V_x, Q_u = l_u + B^T V_x
+        const R Qx0 = lx0 + m::fma_(L.r0, Vx3, Vx0);
+        const R Qx1 = lx1 + m::fma_(L.r1, Vx3, Vx1);
+        const R Qx2 = lx2 + m::fma_(L.r2, Vx3, m::fma_(L.a12, Vx1, m::fma_(L.a02, Vx0, Vx2)));
+        const R Qx3 = lx3 + gam * Vx3;
+        const R Qu0 = lu0 + m::fma_(L.s0, Vx3, m::fma_(L.b10, Vx1, L.b00 * Vx0));
+        const R Qu1 = lu1 + dt * Vx2;
+        // gains: K = -(Q_uu + reg I)^-1 Q_ux, k = -(Q_uu + reg I)^-1 Q_u   (core/ddp.py:239-244)
+        LU2<R> F;
+        lu2_factor(F, Quu00 + reg, Quu01, Quu10, Quu11 + reg);
+        R K00, K01, K02, K03, K10, K11, K12, K13, k0, k1;
+        lu2_solve(F, Qux00, Qux10, K00, K10);
+        lu2_solve(F, Qux01, Qux11, K01, K11);
+        lu2_solve(F, Qux02, Qux12, K02, K12);
+        lu2_solve(F, Qux03, Qux13, K03, K13);
+        lu2_solve(F, Qu0, Qu1, k0, k1);
+        K00 = -K00; K01 = -K01; K02 = -K02; K03 = -K03;
+        K10 = -K10; K11 = -K11; K12 = -K12; K13 = -K13;
+        k0 = -k0; k1 = -k1;
+        {
+            R *o = GK + (8LL * k) * S;
+            o[0 * S] = K00; o[1 * S] = K01; o[2 * S] = K02; o[3 * S] = K03;
+            o[4 * S] = K10; o[5 * S] = K11; o[6 * S] = K12; o[7 * S] = K13;
+            Gk[(2LL * k) * S] = k0;
+            Gk[(2LL * k + 1) * S] = k1;
+        }
+        // V_x = Q_x + K^T Q_uu k + K^T Q_u + Q_xu k   (un-regularised Q_uu, core/ddp.py:251)
+        const R s0 = m::fma_(Quu01, k1, Quu00 * k0) + Qu0;
+        const R s1 = m::fma_(Quu11, k1, Quu10 * k0) + Qu1;
+        Vx0 = Qx0 + m::fma_(K10, s1, K00 * s0) + m::fma_(Qux10, k1, Qux00 * k0);
+        Vx1 = Qx1 + m::fma_(K11, s1, K01 * s0) + m::fma_(Qux11, k1, Qux01 * k0);
+        Vx2 = Qx2 + m::fma_(K12, s1, K02 * s0) + m::fma_(Qux12, k1, Qux02 * k0);
+        Vx3 = Qx3 + m::fma_(K13, s1, K03 * s0) + m::fma_(Qux13, k1, Qux03 * k0);
+        // V_xx = Q_xx + K^T Q_uu K + K^T Q_ux + Q_xu K   (never symmetrised, core/ddp.py:252)
 #define COL_W(j)                                                              \
     const R W0##j = m::fma_(Quu01, K1##j, Quu00 * K0##j) + Qux0##j;           \
     const R W1##j = m::fma_(Quu11, K1##j, Quu10 * K0##j) + Qux1##j;
-                COL_W(0) COL_W(1) COL_W(2) COL_W(3)
+        COL_W(0) COL_W(1) COL_W(2) COL_W(3)
 #undef COL_W
 #define ENT_V(i, j) V##i##j = Qxx##i##j + m::fma_(K1##i, W1##j, K0##i * W0##j) + m::fma_(Qux1##i, K1##j, Qux0##i * K0##j);
-                ENT_V(0, 0) ENT_V(0, 1) ENT_V(0, 2) ENT_V(0, 3)
-                ENT_V(1, 0) ENT_V(1, 1) ENT_V(1, 2) ENT_V(1, 3)
-                ENT_V(2, 0) ENT_V(2, 1) ENT_V(2, 2) ENT_V(2, 3)
-                ENT_V(3, 0) ENT_V(3, 1) ENT_V(3, 2) ENT_V(3, 3)
+        ENT_V(0, 0) ENT_V(0, 1) ENT_V(0, 2) ENT_V(0, 3)
+        ENT_V(1, 0) ENT_V(1, 1) ENT_V(1, 2) ENT_V(1, 3)
+        ENT_V(2, 0) ENT_V(2, 1) ENT_V(2, 2) ENT_V(2, 3)
+        ENT_V(3, 0) ENT_V(3, 1) ENT_V(3, 2) ENT_V(3, 3)
 #undef ENT_V
-                // non-finite guard (reference raises: core/ddp.py:225-254)
-                R chk = (Vx0 + Vx1) + (Vx2 + Vx3) + (k0 + k1) + (K00 + K01) + (K02 + K03) + (K10 + K11) + (K12 + K13) +
-                        (V00 + V11) + (V22 + V33) + (V01 + V02) + (V03 + V12) + (V13 + V23) + (V10 + V20) + (V30 + V21) +
-                        (V31 + V32);
-                bad |= !finite_(chk);
-            }
-
-            // ---- phase F: forward pass, every alpha evaluated (core/ddp.py:256-296) ----
-            Cand<R> cs[DTMPC_MAX_ALPHAS];
-            const OcpT<R> &o = P.ocp[stage];
-            for (int c = 0; c < n_alpha; ++c) {
-                cs[c].x = State<R>{x00, x01, x02, x03, B0};
-                cs[c].J = R(0);
-            }
-            for (int k = 0; k < T; ++k) {
-                const R X0 = WS(wX, 4 * k + 0), X1 = WS(wX, 4 * k + 1), X2 = WS(wX, 4 * k + 2), X3 = WS(wX, 4 * k + 3);
-                const R v0 = WS(wV, 2 * k), v1 = WS(wV, 2 * k + 1);
-                const R K00 = WS(wK, 8 * k + 0), K01 = WS(wK, 8 * k + 1), K02 = WS(wK, 8 * k + 2), K03 = WS(wK, 8 * k + 3);
-                const R K10 = WS(wK, 8 * k + 4), K11 = WS(wK, 8 * k + 5), K12 = WS(wK, 8 * k + 6), K13 = WS(wK, 8 * k + 7);
-                const R k0 = WS(wk, 2 * k), k1 = WS(wk, 2 * k + 1);
-                R r0, r1, r2, q0, q1;
-                REF_AT(k, r0, r1, r2);
-                UREF_AT(k, q0, q1);
-                for (int c = 0; c < n_alpha; ++c) {
-                    const R al = o.alphas[c];
-                    if (al == R(0)) continue;  // current trajectory, cost already known (Jcur)
-                    State<R> x = cs[c].x;
-                    const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
-                    const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
-                    const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-                    R u0 = m::fma_(al, du0, v0), u1 = m::fma_(al, du1, v1);
-                    clamp_u(E, u0, u1);
-                    cs[c].J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r0, r1, r2, q0, q1);
-                    step(E, th, x, u0, u1);
-                    cs[c].x = x;
-                }
-            }
-            int best_c = -1;
-            R best = R(0), second = m::inf_();
-            {
-                R r0, r1, r2;
-                REF_AT(T, r0, r1, r2);
-                for (int c = 0; c < n_alpha; ++c) {
-                    R Jc;
-                    if (o.alphas[c] == R(0)) {
-                        Jc = Jcur;
-                    } else {
-                        const State<R> &x = cs[c].x;
-                        Jc = cs[c].J + terminal_cost(th, x.px, x.py, x.th, x.b, r0, r1, r2);
-                    }
-                    bad |= !finite_(Jc);
-                    if (best_c < 0 || Jc < best) {  // strict '<', first wins (core/ddp.py:293)
-                        if (best_c >= 0) second = m::min_(second, best);
-                        best = Jc;
-                        best_c = c;
-                    } else {
-                        second = m::min_(second, Jc);
-                    }
-                }
-            }
-
-            // ---- phase W: commit the winner (recomputed; candidates are not stored) ----
-            const R aw = o.alphas[best_c];
-            if (aw != R(0) && !bad) {
-                State<R> x{x00, x01, x02, x03, B0};
-                R J = R(0);
-                R X0 = x00, X1 = x01, X2 = x02, X3 = x03;
-                for (int k = 0; k < T; ++k) {
-                    const R v0 = WS(wV, 2 * k), v1 = WS(wV, 2 * k + 1);
-                    const R K00 = WS(wK, 8 * k + 0), K01 = WS(wK, 8 * k + 1), K02 = WS(wK, 8 * k + 2), K03 = WS(wK, 8 * k + 3);
-                    const R K10 = WS(wK, 8 * k + 4), K11 = WS(wK, 8 * k + 5), K12 = WS(wK, 8 * k + 6), K13 = WS(wK, 8 * k + 7);
-                    const R k0 = WS(wk, 2 * k), k1 = WS(wk, 2 * k + 1);
-                    const R N0 = WS(wX, 4 * (k + 1) + 0), N1 = WS(wX, 4 * (k + 1) + 1), N2 = WS(wX, 4 * (k + 1) + 2),
-                            N3 = WS(wX, 4 * (k + 1) + 3);
-                    R r0, r1, r2, q0, q1;
-                    REF_AT(k, r0, r1, r2);
-                    UREF_AT(k, q0, q1);
-                    const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
-                    const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
-                    const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-                    R u0 = m::fma_(aw, du0, v0), u1 = m::fma_(aw, du1, v1);
-                    clamp_u(E, u0, u1);
-                    WS(wV, 2 * k) = u0;
-                    WS(wV, 2 * k + 1) = u1;
-                    J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r0, r1, r2, q0, q1);
-                    step(E, th, x, u0, u1);
-                    WS(wX, 4 * (k + 1) + 0) = x.px;
-                    WS(wX, 4 * (k + 1) + 1) = x.py;
-                    WS(wX, 4 * (k + 1) + 2) = x.th;
-                    WS(wX, 4 * (k + 1) + 3) = x.b;
-                    X0 = N0; X1 = N1; X2 = N2; X3 = N3;
-                }
-                R r0, r1, r2;
-                REF_AT(T, r0, r1, r2);
-                J += terminal_cost(th, x.px, x.py, x.th, x.b, r0, r1, r2);
-                Jcur = J;
-            }
-
-            // ---- bookkeeping: trace, tolerance break (core/ddp.py:301-305) ----
-            const SolveArgs<R> &a = P.io[stage];
-            if (!bad) {
-                if (a.alpha_idx != nullptr) a.alpha_idx[inst * o.max_iter + it] = best_c;
-                if (a.costs != nullptr) a.costs[inst * o.max_iter + it] = best;
-                if (a.margins != nullptr) a.margins[inst * o.max_iter + it] = second - best;
-                ++it;
-            }
-            const bool conv = have_prev && (m::abs_(prev - best) < tol);
-            prev = best;
-            have_prev = true;
-            if (bad || conv || it >= max_iter) finish_stage(bad ? DTMPC_ST_NONFINITE : 0);
-        }
+        // non-finite guard (the reference raises: core/ddp.py:225-254)
+        const R chk = (Vx0 + Vx1) + (Vx2 + Vx3) + (k0 + k1) + (K00 + K01) + (K02 + K03) + (K10 + K11) + (K12 + K13) +
+                      (V00 + V11) + (V22 + V33) + (V01 + V02) + (V03 + V12) + (V13 + V23) + (V10 + V20) + (V30 + V21) +
+                      (V31 + V32);
+        bad |= !finite_(chk);
     }
-#undef WS
-#undef REF_AT
-#undef UREF_AT
+    if (bad) P.ws.flags[i] |= 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward line search (core/ddp.py:256-290): blockDim = (32, n_eval); warp y rolls out candidate y for the 32
+// instances of the CTA, so the CTA touches each gain / trajectory row once for all candidates.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> __global__ void fwd_kernel(const __grid_constant__ SolveParams<R> P) {
+    using m = M<R>;
+    const int n_act = P.ws.counts[P.parity];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    if (j >= n_act) return;
+    const int c = threadIdx.y;
+    const long long i = P.ws.list[P.parity][j];
+    const long long S = P.B;
+    const EnvT<R> &E = P.env;
+    const int T = P.ocp.T;
+    const int a_idx = P.eval_idx[c];
+    const R al = P.ocp.alphas[a_idx];
+    Theta<R> th;
+    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+    R t0 = R(0), t1 = R(0), t2 = R(0);
+    if (!P.use_ref) {
+        const R *tp = P.io.target + i * P.io.target_stride;
+        t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
+    }
+    const int bc = P.ws.cur[i];
+    const int slot = c < bc ? c : c + 1;
+    const R *X = P.ws.traj + (long long)bc * traj_rows(T) * S + i;
+    const R *V = X + 4LL * (T + 1) * S;
+    R *Xn = P.ws.traj + (long long)slot * traj_rows(T) * S + i;
+    R *Vn = Xn + 4LL * (T + 1) * S;
+    const R *GK = P.ws.gains + i;
+    const R *Gk = GK + 8LL * T * S;
+
+    State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
+    Xn[0 * S] = x.px; Xn[1 * S] = x.py; Xn[2 * S] = x.th; Xn[3 * S] = x.b;
+    R J = R(0);
+    // Inputs of one step; the next step's inputs are fetched while the current step computes (register double
+    // buffering): the loads do not depend on the rollout, and a step is ~2k issue cycles, so one step of lookahead
+    // covers the DRAM latency that otherwise stalls every warp at the top of each step.
+    struct StepIn {
+        R X0, X1, X2, X3, v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1;
+        RefPt<R> r;
+    };
+    auto load_step = [&](int k, StepIn &q) {
+        q.X0 = X[(4LL * k + 0) * S]; q.X1 = X[(4LL * k + 1) * S]; q.X2 = X[(4LL * k + 2) * S]; q.X3 = X[(4LL * k + 3) * S];
+        q.v0 = V[(2LL * k) * S]; q.v1 = V[(2LL * k + 1) * S];
+        const R *o = GK + (8LL * k) * S;
+        q.K00 = o[0 * S]; q.K01 = o[1 * S]; q.K02 = o[2 * S]; q.K03 = o[3 * S];
+        q.K10 = o[4 * S]; q.K11 = o[5 * S]; q.K12 = o[6 * S]; q.K13 = o[7 * S];
+        q.k0 = Gk[(2LL * k) * S]; q.k1 = Gk[(2LL * k + 1) * S];
+        ref_at(P, i, k, true, t0, t1, t2, q.r);
+    };
+    StepIn in;
+    load_step(0, in);
+    for (int k = 0; k < T; ++k) {
+        StepIn nx;
+        load_step(k + 1 < T ? k + 1 : k, nx);
+        // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
+        const R d0 = x.px - in.X0, d1 = x.py - in.X1, d2 = x.th - in.X2, d3 = x.b - in.X3;
+        const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
+        const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
+        R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
+        clamp_u(E, u0, u1);
+        Vn[(2LL * k) * S] = u0;
+        Vn[(2LL * k + 1) * S] = u1;
+        J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, in.r.x0, in.r.x1, in.r.x2, in.r.u0, in.r.u1);
+        step(E, th, x, u0, u1);
+        Xn[(4LL * (k + 1) + 0) * S] = x.px;
+        Xn[(4LL * (k + 1) + 1) * S] = x.py;
+        Xn[(4LL * (k + 1) + 2) * S] = x.th;
+        Xn[(4LL * (k + 1) + 3) * S] = x.b;
+        in = nx;
+    }
+    RefPt<R> r;
+    ref_at(P, i, T, false, t0, t1, t2, r);
+    J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
+    P.ws.J[(long long)a_idx * S + i] = J;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// selection (core/ddp.py:293-305): strict '<' in list order, tolerance break on the accepted costs, compaction
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(LS_BLOCK) sel_kernel(const __grid_constant__ SolveParams<R> P) {
+    using m = M<R>;
+    const int n_act = P.ws.counts[P.parity];
+    const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
+    bool keep = false;
+    long long i = -1;
+    if (j < n_act) {
+        i = P.ws.list[P.parity][j];
+        const long long S = P.B;
+        const OcpT<R> &o = P.ocp;
+        const R Jc = P.ws.Jcur[i];
+        bool bad = (P.ws.flags[i] & 1) != 0;
+        int best_c = -1;
+        R best = R(0), second = m::inf_();
+        for (int c = 0; c < o.n_alpha; ++c) {
+            const R v = (o.alphas[c] == R(0)) ? Jc : P.ws.J[(long long)c * S + i];
+            bad |= !finite_(v);
+            if (best_c < 0 || v < best) {
+                if (best_c >= 0) second = m::min_(second, best);
+                best = v;
+                best_c = c;
+            } else {
+                second = m::min_(second, v);
+            }
+        }
+        int it = P.ws.it[i];
+        bool done = true;
+        if (!bad) {
+            if (o.alphas[best_c] != R(0)) {
+                int e = 0;
+                for (int q = 0; q < P.n_eval; ++q)
+                    if (P.eval_idx[q] == best_c) e = q;
+                const int bc = P.ws.cur[i];
+                P.ws.cur[i] = e < bc ? e : e + 1;
+                P.ws.Jcur[i] = best;
+            }
+            if (P.io.alpha_idx) P.io.alpha_idx[i * o.max_iter + it] = best_c;
+            if (P.io.costs) P.io.costs[i * o.max_iter + it] = best;
+            if (P.io.margins) P.io.margins[i * o.max_iter + it] = second - best;
+            const bool conv = it > 0 && (m::abs_(P.ws.prev[i] - best) < o.tol);
+            P.ws.prev[i] = best;
+            ++it;
+            P.ws.it[i] = it;
+            done = conv || it >= o.max_iter;
+        } else {
+            P.io.status[i] |= DTMPC_ST_NONFINITE << P.status_shift;
+        }
+        keep = !done;
+    }
+    // order-preserving-within-warp compaction into the other list
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (mask) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == (__ffs(mask) - 1)) base = atomicAdd(&P.ws.counts[P.parity ^ 1], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+        if (keep) P.ws.list[P.parity ^ 1][base + __popc(mask & ((1u << lane) - 1u))] = (int)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// results: instance-major copies of the accepted trajectory (and gains); nominal solution -> auxiliary reference
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(LS_BLOCK) out_kernel(const __grid_constant__ SolveParams<R> P) {
+    const long long i = (long long)blockIdx.x * LS_BLOCK + threadIdx.x;
+    if (i >= P.B) return;
+    const long long S = P.B;
+    const int T = P.ocp.T;
+    const R *X = P.ws.traj + (long long)P.ws.cur[i] * traj_rows(T) * S + i;
+    const R *V = X + 4LL * (T + 1) * S;
+    R *Xo = P.io.X + i * (4LL * (T + 1));
+    R *Vo = P.io.V + i * (2LL * T);
+    for (int r = 0; r < 4 * (T + 1); ++r) Xo[r] = X[(long long)r * S];
+    for (int r = 0; r < 2 * T; ++r) Vo[r] = V[(long long)r * S];
+    if (P.write_ref) {
+        for (int k = 0; k <= T; ++k) {
+            P.ws.ref[(3LL * k + 0) * S + i] = X[(4LL * k + 0) * S];
+            P.ws.ref[(3LL * k + 1) * S + i] = X[(4LL * k + 1) * S];
+            P.ws.ref[(3LL * k + 2) * S + i] = X[(4LL * k + 2) * S];
+        }
+        for (int r = 0; r < 2 * T; ++r) P.ws.ref[(3LL * (T + 1) + r) * S + i] = V[(long long)r * S];
+    }
+    if (P.io.K) {
+        R *Ko = P.io.K + i * (8LL * T);
+        for (int r = 0; r < 8 * T; ++r) Ko[r] = P.ws.gains[(long long)r * S + i];
+    }
+    if (P.io.kff) {
+        R *ko = P.io.kff + i * (2LL * T);
+        for (int r = 0; r < 2 * T; ++r) ko[r] = P.ws.gains[(8LL * T + r) * S + i];
+    }
+    if (P.io.iters) P.io.iters[i] = P.ws.it[i];
 }
 
 }  // namespace dtmpc

@@ -149,7 +149,7 @@ def ilqr_solve_batched(system: SystemSpec, ocp: OcpSpec, x0: Tensor, V_init: Ten
     env_c, ocp_c = system.to_c(), ocp.to_c()
     ws = workspace or default_workspace(device)
     with torch.cuda.device(device):
-        nbytes = L.dtmpc_solve_workspace_bytes(T, B, 0, x0.element_size())
+        nbytes = L.dtmpc_solve_workspace_bytes(T, B, ocp_c.n_alpha, x0.element_size())
         buf = ws.get("solve", nbytes)
         rc = getattr(L, f"dtmpc_ilqr_solve_{sfx}")(C.byref(env_c), C.byref(ocp_c), B, C.byref(io), _ptr(buf),
                                                    buf.numel(), _stream())
@@ -184,7 +184,7 @@ def tube_solve_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec,
     env_c, n_c, a_c = system.to_c(), nominal.to_c(), auxiliary.to_c()
     ws = workspace or default_workspace(device)
     with torch.cuda.device(device):
-        nbytes = L.dtmpc_solve_workspace_bytes(T, B, 1, x0_nom.element_size())
+        nbytes = L.dtmpc_solve_workspace_bytes(T, B, max(n_c.n_alpha, a_c.n_alpha), x0_nom.element_size())
         buf = ws.get("solve", nbytes)
         rc = getattr(L, f"dtmpc_tube_solve_{sfx}")(C.byref(env_c), C.byref(n_c), C.byref(a_c), B, C.byref(ion),
                                                    C.byref(ioa), _ptr(buf), buf.numel(), _stream())

@@ -128,8 +128,9 @@ typedef struct dtmpc_sens_io {
 int dtmpc_abi_version(void);
 const char *dtmpc_last_error(void);
 
-/* Scratch sizes in bytes (elem_size 8 or 4).  Need a CUDA device (SM count). */
-size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t tube, int32_t elem_size);
+/* Scratch sizes in bytes (elem_size 8 or 4); pure functions of their arguments (no device needed).
+ * n_alpha = number of line-search step sizes (the larger of the two OCPs for a tube solve). */
+size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size);
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size);
 size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size);
 
@@ -140,7 +141,7 @@ int dtmpc_ilqr_solve_f64(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, 
 int dtmpc_ilqr_solve_f32(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_solve_io *io,
                          void *workspace, size_t workspace_bytes, void *stream);
 
-/* Two-layer tube MPC in one launch: nominal solve, then the auxiliary solve tracking the nominal
+/* Two-layer tube MPC in one call: nominal solve, then the auxiliary solve tracking the nominal
  * solution of the same instance -- reference core/tube_mpc.py:844-909 (paper) / :305-399 (full).
  * aux->Xref/Uref are ignored. status = nominal bits | auxiliary bits << 4. */
 int dtmpc_tube_solve_f64(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,

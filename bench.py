@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--dtype", type=str, default="f64", choices=["f64", "f32"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warmup-seconds", type=float, default=2.0, help="minimum warm-up wall time (clock ramp)")
     args = ap.parse_args()
 
     from differentiable_tube_mpc_b200 import default_dubins_config
@@ -289,7 +290,7 @@ def main():
     # warm-up: at least W (>= 3) steps AND ~2 s of load -- the first launches pay lazy module loading and the SM
     # clocks need a few hundred ms to ramp from idle (first two steps measured 2-9x slower than steady state)
     n_warm, t_warm = 0, time.perf_counter()
-    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_warm) < 2.0:
+    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_warm) < args.warmup_seconds:
         device_step()
         torch.cuda.synchronize()
         n_warm += 1

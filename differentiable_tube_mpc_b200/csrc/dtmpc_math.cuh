@@ -16,14 +16,101 @@
 
 #include "../../include/dtmpc.h"
 
+#include "dtmpc_fastmath_coeffs.inc"
+
 namespace dtmpc {
+
+// ---------------------------------------------------------------------------
+// fp64 exp / log / sincos with their polynomial coefficients in __constant__ memory.
+// libdevice carries fp64 coefficients as 64-bit immediates; sm_100a has no 64-bit immediate operand, so every use
+// costs two UMOV + two MOV on top of the DFMA (measured: 236 UMOV + 160 MOV of 1750 issued instructions per
+// line-search step, profiles/r01b).  A constant-bank operand is free.  Accuracy: <= 2 ulp on the argument ranges
+// the path uses (tools/gen_fastmath.py prints the fit errors); outside them the functions defer to libdevice.
+// ---------------------------------------------------------------------------
+namespace fm {
+__constant__ double EXP_C[DTMPC_EXP_N] = {DTMPC_EXP_COEFFS};
+__constant__ double LOG_C[DTMPC_LOG_N] = {DTMPC_LOG_COEFFS};
+__constant__ double SIN_C[DTMPC_SIN_N] = {DTMPC_SIN_COEFFS};
+__constant__ double COS_C[DTMPC_COS_N] = {DTMPC_COS_COEFFS};
+__constant__ double K[12] = {DTMPC_LOG2E, -DTMPC_LN2_HI, -DTMPC_LN2_LO, DTMPC_LN2_HI, DTMPC_LN2_LO, DTMPC_2OPI,
+                             -DTMPC_PIO2_1, -DTMPC_PIO2_2, -DTMPC_PIO2_3, 0x1.8p52, 0x1.6a09e667f3bcdp+0, 0.0};
+enum { LOG2E = 0, NLN2_HI, NLN2_LO, LN2_HI, LN2_LO, TWO_OPI, NPIO2_1, NPIO2_2, NPIO2_3, MAGIC, SQRT2 };
+
+// exp(x) for x <= ~709; x < -700 flushes to 0 (the path only exponentiates z_i - z_max <= 0)
+__device__ __forceinline__ double exp_d(double x) {
+    const double t = ::fma(x, K[LOG2E], K[MAGIC]);
+    const int k = __double2loint(t);
+    const double kf = t - K[MAGIC];
+    double r = ::fma(kf, K[NLN2_HI], x);
+    r = ::fma(kf, K[NLN2_LO], r);
+    double p = EXP_C[0];
+#pragma unroll
+    for (int j = 1; j < DTMPC_EXP_N; ++j) p = ::fma(p, r, EXP_C[j]);
+    double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    if (x < -700.0) res = 0.0;
+    if (!(x <= 709.0)) res = ::exp(x);  // overflow range, NaN: never on the hot path
+    return res;
+}
+
+// log(s) for positive normal s (the path calls it with s = sum of exp(<= 0) in [1, n_obs])
+__device__ __forceinline__ double log_d(double s) {
+    if (!(s >= 2.2250738585072014e-308 && s < __longlong_as_double(0x7ff0000000000000LL))) return ::log(s);
+    const int hi = __double2hiint(s);
+    int e = (hi >> 20) - 1023;
+    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
+    if (m > K[SQRT2]) {
+        m *= 0.5;
+        e += 1;
+    }
+    const double u = (m - 1.0) / (m + 1.0);
+    const double w = u * u;
+    double p = LOG_C[0];
+#pragma unroll
+    for (int j = 1; j < DTMPC_LOG_N; ++j) p = ::fma(p, w, LOG_C[j]);
+    const double u2 = u + u;
+    const double lm = ::fma(u2 * w, p, u2);  // 2 atanh(u)
+    const double ef = (double)e;
+    return ::fma(ef, K[LN2_HI], lm) + ef * K[LN2_LO];
+}
+
+__device__ __forceinline__ void sincos_d(double x, double *sp, double *cp) {
+    if (!(::fabs(x) < 1.0e5)) {  // large arguments, inf, NaN: libdevice (Payne-Hanek)
+        ::sincos(x, sp, cp);
+        return;
+    }
+    const double t = ::fma(x, K[TWO_OPI], K[MAGIC]);
+    const int q = __double2loint(t);
+    const double qf = t - K[MAGIC];
+    double r = ::fma(qf, K[NPIO2_1], x);
+    r = ::fma(qf, K[NPIO2_2], r);
+    r = ::fma(qf, K[NPIO2_3], r);
+    const double w = r * r;
+    double ps = SIN_C[0], pc = COS_C[0];
+#pragma unroll
+    for (int j = 1; j < DTMPC_SIN_N; ++j) ps = ::fma(ps, w, SIN_C[j]);
+#pragma unroll
+    for (int j = 1; j < DTMPC_COS_N; ++j) pc = ::fma(pc, w, COS_C[j]);
+    const double sn = ::fma(r * w, ps, r);
+    const double cs = ::fma(w * w, pc, ::fma(-0.5, w, 1.0));
+    const double a = (q & 1) ? cs : sn;
+    const double b = (q & 1) ? sn : cs;
+    *sp = (q & 2) ? -a : a;
+    *cp = ((q + 1) & 2) ? -b : b;
+}
+}  // namespace fm
 
 template <typename R> struct M;  // math dispatch
 template <> struct M<double> {
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return ::fma(a, b, c); }
+#ifdef DTMPC_LIBDEVICE_MATH
     static __device__ __forceinline__ double exp_(double x) { return ::exp(x); }
     static __device__ __forceinline__ double log_(double x) { return ::log(x); }
     static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { ::sincos(x, s, c); }
+#else
+    static __device__ __forceinline__ double exp_(double x) { return fm::exp_d(x); }
+    static __device__ __forceinline__ double log_(double x) { return fm::log_d(x); }
+    static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { fm::sincos_d(x, s, c); }
+#endif
     static __device__ __forceinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double max_(double a, double b) { return ::fmax(a, b); }
     static __device__ __forceinline__ double min_(double a, double b) { return ::fmin(a, b); }
@@ -138,24 +225,52 @@ __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx
         }
         return;
     }
-    R zmax = -m::inf_();
+    // Smooth-min.  One pass finds the two largest z_i = -beta h_i (with their 2(p - c_i)) and the third largest
+    // value.  exp(z_i - z_1) <= e^-40 = 4e-18 cannot change sum >= 1 in fp64, so when the third largest is out of
+    // reach (almost always: it needs three obstacles within 2/beta of each other in h) the log-sum-exp has two terms
+    // and costs ONE exp instead of n; otherwise the full ordered sum of the reference is evaluated.  The choice
+    // depends only on this lane's own point, so h stays a pure function of its argument (bitwise reproducible
+    // whatever the neighbouring lanes do).
+    R z1 = -m::inf_(), z2 = -m::inf_(), z3 = -m::inf_();
+    R ax1 = R(0), ay1 = R(0), ax2 = R(0), ay2 = R(0);
     for (int i = 0; i < n; ++i) {
-        R dx = px - e.cx[i], dy = py - e.cy[i];
-        R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
-        zmax = m::max_(zmax, e.nbeta * hi);
-    }
-    R s = R(0), sx = R(0), sy = R(0);
-    for (int i = 0; i < n; ++i) {
-        R dx = px - e.cx[i], dy = py - e.cy[i];
-        R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
-        R w = m::exp_(e.nbeta * hi - zmax);
-        s += w;
+        const R dx = px - e.cx[i], dy = py - e.cy[i];
+        const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+        const R z = e.nbeta * hi;
+        const bool p1 = z > z1, p2 = z > z2, p3 = z > z3;
+        z3 = p2 ? z2 : (p3 ? z : z3);
+        z2 = p1 ? z1 : (p2 ? z : z2);
+        z1 = p1 ? z : z1;
         if (GRAD) {
-            sx = m::fma_(w, R(2) * dx, sx);
-            sy = m::fma_(w, R(2) * dy, sy);
+            ax2 = p1 ? ax1 : (p2 ? dx : ax2);
+            ay2 = p1 ? ay1 : (p2 ? dy : ay2);
+            ax1 = p1 ? dx : ax1;
+            ay1 = p1 ? dy : ay1;
         }
     }
-    h = e.ninv_beta * (zmax + m::log_(s));
+    const R reach = sizeof(R) == 8 ? R(-40) : R(-18);
+    R s, sx = R(0), sy = R(0);
+    if (z3 - z1 > reach) {
+        s = R(0);
+        for (int i = 0; i < n; ++i) {
+            const R dx = px - e.cx[i], dy = py - e.cy[i];
+            const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+            const R w = m::exp_(e.nbeta * hi - z1);
+            s += w;
+            if (GRAD) {
+                sx = m::fma_(w, R(2) * dx, sx);
+                sy = m::fma_(w, R(2) * dy, sy);
+            }
+        }
+    } else {
+        const R e2 = m::exp_(z2 - z1);  // 0 for a single obstacle (z2 = -inf)
+        s = R(1) + e2;
+        if (GRAD) {
+            sx = m::fma_(e2, R(2) * ax2, R(2) * ax1);
+            sy = m::fma_(e2, R(2) * ay2, R(2) * ay1);
+        }
+    }
+    h = e.ninv_beta * (z1 + m::log_(s));
     if (GRAD) {
         gx = sx / s;
         gy = sy / s;

@@ -341,7 +341,13 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
 // forward line search (core/ddp.py:256-290): blockDim = (32, n_eval); warp y rolls out candidate y for the 32
 // instances of the CTA, so the CTA touches each gain / trajectory row once for all candidates.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void fwd_kernel(const __grid_constant__ SolveParams<R> P) {
+#ifndef DTMPC_FWD_PREFETCH
+#define DTMPC_FWD_PREFETCH 0
+#endif
+#ifndef DTMPC_FWD_MAXNREG
+#define DTMPC_FWD_MAXNREG 255
+#endif
+template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * 32 + threadIdx.x;
@@ -388,11 +394,36 @@ template <typename R> __global__ void fwd_kernel(const __grid_constant__ SolvePa
         q.k0 = Gk[(2LL * k) * S]; q.k1 = Gk[(2LL * k + 1) * S];
         ref_at(P, i, k, true, t0, t1, t2, q.r);
     };
+#if DTMPC_FWD_PREFETCH == 1
+    // L1 prefetch hints two steps ahead, one row per warp in turn: the 6 candidate warps of the CTA read the same rows
+    auto prefetch_step = [&](int k) {
+        if (k >= T) return;
+        const int ne = blockDim.y;
+        for (int r = c; r < 21; r += ne) {
+            const R *p;
+            if (r < 4) p = X + (4LL * k + r) * S;
+            else if (r < 6) p = V + (2LL * k + (r - 4)) * S;
+            else if (r < 14) p = GK + (8LL * k + (r - 6)) * S;
+            else if (r < 16) p = Gk + (2LL * k + (r - 14)) * S;
+            else if (!P.use_ref) break;
+            else if (r < 19) p = P.ws.ref + (3LL * k + (r - 16)) * S + i;
+            else p = P.ws.ref + (3LL * (T + 1) + 2LL * k + (r - 19)) * S + i;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        }
+    };
+    prefetch_step(1);
+    StepIn in;
+    for (int k = 0; k < T; ++k) {
+        prefetch_step(k + 2);
+        load_step(k, in);
+        StepIn nx;
+#else
     StepIn in;
     load_step(0, in);
     for (int k = 0; k < T; ++k) {
         StepIn nx;
         load_step(k + 1 < T ? k + 1 : k, nx);
+#endif
         // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
         const R d0 = x.px - in.X0, d1 = x.py - in.X1, d2 = x.th - in.X2, d3 = x.b - in.X3;
         const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
@@ -407,7 +438,11 @@ template <typename R> __global__ void fwd_kernel(const __grid_constant__ SolvePa
         Xn[(4LL * (k + 1) + 1) * S] = x.py;
         Xn[(4LL * (k + 1) + 2) * S] = x.th;
         Xn[(4LL * (k + 1) + 3) * S] = x.b;
+#if DTMPC_FWD_PREFETCH != 1
         in = nx;
+#else
+        (void)nx;
+#endif
     }
     RefPt<R> r;
     ref_at(P, i, T, false, t0, t1, t2, r);

@@ -103,17 +103,17 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
     const size_t nB = (size_t)B;
     char *counts = take(256);
     char *l0 = take(nB * sizeof(int)), *l1 = take(nB * sizeof(int));
-    char *cur = take(nB * sizeof(int)), *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
+    char *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
     char *Jcur = take(nB * sizeof(R)), *prev = take(nB * sizeof(R)), *B0 = take(nB * sizeof(R));
     char *J = take(nB * sizeof(R) * (size_t)n_alpha);
-    char *traj = take(nB * sizeof(R) * (size_t)traj_rows(T) * (size_t)(n_alpha + 1));
+    char *traj = take(nB * sizeof(R) * (size_t)traj_rows(T));
     char *gains = take(nB * sizeof(R) * 10 * (size_t)T);
     char *lin = take(nB * sizeof(R) * 8 * (size_t)T);
     char *ref = take(nB * sizeof(R) * (size_t)ref_rows(T));
     if (w) {
         w->counts = (int *)counts;
         w->list[0] = (int *)l0; w->list[1] = (int *)l1;
-        w->cur = (int *)cur; w->it = (int *)it; w->flags = (int *)flags;
+        w->it = (int *)it; w->flags = (int *)flags;
         w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0; w->J = (R *)J;
         w->traj = (R *)traj; w->gains = (R *)gains; w->lin = (R *)lin; w->ref = (R *)ref;
     }

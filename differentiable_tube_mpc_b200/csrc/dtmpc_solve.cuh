@@ -9,14 +9,16 @@
 //   ric_kernel   thread per instance               backward Riccati sweep, register-resident V_x / V_xx, gains K, k
 //   fwd_kernel   thread per (instance, candidate)  forward line search: every alpha != 0 rolls out in its own lane,
 //                                                  one warp per candidate, 32 instances per CTA, so the gains and the
-//                                                  current trajectory are fetched once per CTA (L1) for all candidates
+//                                                  current trajectory are fetched once per CTA (L1) for all candidates;
+//                                                  only the candidate COST leaves the kernel
 //   sel_kernel   thread per instance               argmin (strict <, first wins), tolerance break, trace, compaction
-//                                                  of the active list
+//                                                  of the active list, and the commit: the winner is rolled out once
+//                                                  more, in place (bit-identical to its candidate, dtmpc_math.cuh)
 //
-// Candidates write their trajectories into per-candidate buffers; accepting a step is an index update (`cur`), nothing
-// is recomputed or copied.  The alpha = 0 candidate is the current trajectory bit for bit (dtmpc_math.cuh) and costs
-// nothing.  Instances that have converged leave the active list, so warps stay full while iteration counts differ
-// (reference: 2..20 iterations per instance).
+// Candidate trajectories are never stored: storing all of them made the line search HBM-bound (2.6 GB per iteration
+// at B = 65,536, profiles/r01b), recomputing the winner costs 1/n_alpha more arithmetic and keeps one trajectory per
+// instance.  The alpha = 0 candidate is the current trajectory bit for bit and costs nothing.  Instances that have
+// converged leave the active list, so warps stay full while iteration counts differ (reference: 2..20 per instance).
 //
 // Scratch is instance-minor structure-of-arrays (row r of instance i at base[r*B + i]): every access of a warp is a
 // contiguous segment.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
@@ -36,12 +38,11 @@ template <typename R> struct SolveArgs {
 template <typename R> struct SolveWs {
     int *counts;     // [2] sizes of the two active lists
     int *list[2];    // active instance indices (double buffered)
-    int *cur;        // [B] buffer holding the current trajectory
     int *it;         // [B] completed iterations
     int *flags;      // [B] bit 0: non-finite in the backward pass
     R *Jcur, *prev, *B0;  // [B] cost of the current trajectory, previous accepted cost, B(h(x0) - tight)
     R *J;            // [n_alpha][B] candidate costs
-    R *traj;         // [n_buf][4(T+1)+2T][B]
+    R *traj;         // [4(T+1)+2T][B] current trajectory X, V
     R *gains;        // [10T][B]  K (8 rows per k) then k (2 rows per k)
     R *lin;          // [8T][B]
     R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)
@@ -142,7 +143,6 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
     P.ws.Jcur[i] = J;
     P.ws.prev[i] = R(0);
-    P.ws.cur[i] = 0;
     P.ws.it[i] = 0;
     P.ws.flags[i] = 0;
     P.ws.list[0][i] = (int)i;
@@ -164,7 +164,7 @@ template <typename R> __global__ void __launch_bounds__(256) lin_kernel(const __
     const EnvT<R> &E = P.env;
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
-    const R *X = P.ws.traj + (long long)P.ws.cur[i] * traj_rows(T) * S + i;
+    const R *X = P.ws.traj + i;
     const R *V = X + 4LL * (T + 1) * S;
     const R pth = X[(4LL * k + 2) * S];
     const R v = V[(2LL * k) * S];
@@ -197,7 +197,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
-    const R *X = P.ws.traj + (long long)P.ws.cur[i] * traj_rows(T) * S + i;
+    const R *X = P.ws.traj + i;
     const R *V = X + 4LL * (T + 1) * S;
     const R *LN = P.ws.lin + i;
     R *GK = P.ws.gains + i;
@@ -366,17 +366,12 @@ template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
-    const int bc = P.ws.cur[i];
-    const int slot = c < bc ? c : c + 1;
-    const R *X = P.ws.traj + (long long)bc * traj_rows(T) * S + i;
+    const R *X = P.ws.traj + i;
     const R *V = X + 4LL * (T + 1) * S;
-    R *Xn = P.ws.traj + (long long)slot * traj_rows(T) * S + i;
-    R *Vn = Xn + 4LL * (T + 1) * S;
     const R *GK = P.ws.gains + i;
     const R *Gk = GK + 8LL * T * S;
 
     State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
-    Xn[0 * S] = x.px; Xn[1 * S] = x.py; Xn[2 * S] = x.th; Xn[3 * S] = x.b;
     R J = R(0);
     // Inputs of one step; the next step's inputs are fetched while the current step computes (register double
     // buffering): the loads do not depend on the rollout, and a step is ~2k issue cycles, so one step of lookahead
@@ -430,14 +425,8 @@ template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(
         const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
         R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
         clamp_u(E, u0, u1);
-        Vn[(2LL * k) * S] = u0;
-        Vn[(2LL * k + 1) * S] = u1;
         J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, in.r.x0, in.r.x1, in.r.x2, in.r.u0, in.r.u1);
         step(E, th, x, u0, u1);
-        Xn[(4LL * (k + 1) + 0) * S] = x.px;
-        Xn[(4LL * (k + 1) + 1) * S] = x.py;
-        Xn[(4LL * (k + 1) + 2) * S] = x.th;
-        Xn[(4LL * (k + 1) + 3) * S] = x.b;
 #if DTMPC_FWD_PREFETCH != 1
         in = nx;
 #else
@@ -448,6 +437,45 @@ template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(
     ref_at(P, i, T, false, t0, t1, t2, r);
     J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
     P.ws.J[(long long)a_idx * S + i] = J;
+}
+
+// Rolls the accepted candidate out once more and overwrites the instance's trajectory in place (X_k of the old
+// trajectory is read before x_{k+1} of the new one lands in the next row).
+template <typename R> __device__ __forceinline__ void commit_candidate(const SolveParams<R> &P, long long i, R al) {
+    using m = M<R>;
+    const long long S = P.B;
+    const EnvT<R> &E = P.env;
+    const int T = P.ocp.T;
+    Theta<R> th;
+    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+    R *X = P.ws.traj + i;
+    R *V = X + 4LL * (T + 1) * S;
+    const R *GK = P.ws.gains + i;
+    const R *Gk = GK + 8LL * T * S;
+    State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
+    R X0 = x.px, X1 = x.py, X2 = x.th, X3 = x.b;
+    for (int k = 0; k < T; ++k) {
+        const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
+        const R *o = GK + (8LL * k) * S;
+        const R K00 = o[0 * S], K01 = o[1 * S], K02 = o[2 * S], K03 = o[3 * S];
+        const R K10 = o[4 * S], K11 = o[5 * S], K12 = o[6 * S], K13 = o[7 * S];
+        const R k0 = Gk[(2LL * k) * S], k1 = Gk[(2LL * k + 1) * S];
+        const R N0 = X[(4LL * (k + 1) + 0) * S], N1 = X[(4LL * (k + 1) + 1) * S], N2 = X[(4LL * (k + 1) + 2) * S],
+                N3 = X[(4LL * (k + 1) + 3) * S];
+        const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
+        const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
+        const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
+        R u0 = m::fma_(al, du0, v0), u1 = m::fma_(al, du1, v1);
+        clamp_u(E, u0, u1);
+        V[(2LL * k) * S] = u0;
+        V[(2LL * k + 1) * S] = u1;
+        step(E, th, x, u0, u1);
+        X[(4LL * (k + 1) + 0) * S] = x.px;
+        X[(4LL * (k + 1) + 1) * S] = x.py;
+        X[(4LL * (k + 1) + 2) * S] = x.th;
+        X[(4LL * (k + 1) + 3) * S] = x.b;
+        X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -482,11 +510,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) sel_kernel(con
         bool done = true;
         if (!bad) {
             if (o.alphas[best_c] != R(0)) {
-                int e = 0;
-                for (int q = 0; q < P.n_eval; ++q)
-                    if (P.eval_idx[q] == best_c) e = q;
-                const int bc = P.ws.cur[i];
-                P.ws.cur[i] = e < bc ? e : e + 1;
+                commit_candidate(P, i, o.alphas[best_c]);
                 P.ws.Jcur[i] = best;
             }
             if (P.io.alpha_idx) P.io.alpha_idx[i * o.max_iter + it] = best_c;
@@ -521,7 +545,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) out_kernel(con
     if (i >= P.B) return;
     const long long S = P.B;
     const int T = P.ocp.T;
-    const R *X = P.ws.traj + (long long)P.ws.cur[i] * traj_rows(T) * S + i;
+    const R *X = P.ws.traj + i;
     const R *V = X + 4LL * (T + 1) * S;
     R *Xo = P.io.X + i * (4LL * (T + 1));
     R *Vo = P.io.V + i * (2LL * T);

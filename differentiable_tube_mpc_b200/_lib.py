@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdtmpc_b200.so")
+# DTMPC_LIB selects an alternative build of the same ABI (kernel tuning experiments); default: the in-tree library
+LIB_PATH = os.environ.get("DTMPC_LIB") or os.path.join(_HERE, "libdtmpc_b200.so")
 
 MAX_OBS = 16
 MAX_ALPHAS = 8

@@ -342,10 +342,10 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
 // instances of the CTA, so the CTA touches each gain / trajectory row once for all candidates.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef DTMPC_FWD_PREFETCH
-#define DTMPC_FWD_PREFETCH 0
+#define DTMPC_FWD_PREFETCH 2
 #endif
 #ifndef DTMPC_FWD_MAXNREG
-#define DTMPC_FWD_MAXNREG 255
+#define DTMPC_FWD_MAXNREG 104
 #endif
 template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
@@ -412,6 +412,11 @@ template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(
         prefetch_step(k + 2);
         load_step(k, in);
         StepIn nx;
+#elif DTMPC_FWD_PREFETCH == 2
+    StepIn in;
+    for (int k = 0; k < T; ++k) {
+        load_step(k, in);
+        StepIn nx;
 #else
     StepIn in;
     load_step(0, in);
@@ -427,7 +432,7 @@ template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(
         clamp_u(E, u0, u1);
         J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, in.r.x0, in.r.x1, in.r.x2, in.r.u0, in.r.u1);
         step(E, th, x, u0, u1);
-#if DTMPC_FWD_PREFETCH != 1
+#if DTMPC_FWD_PREFETCH == 0
         in = nx;
 #else
         (void)nx;

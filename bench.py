@@ -82,45 +82,64 @@ def algorithmic_bytes_per_solve(T, full):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: in-process NVML every 50 ms (an `nvidia-smi -lms`
+    subprocess perturbed the measured step time by ~30 %); falls back to nvidia-smi if NVML is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.power = [], set(), []
+        self.smax = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.h = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[0].isdigit() else self.gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return self._smi_once()
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "source": "nvml"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(v) for v in out.strip().split(",")]
+            return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 def measured_peaks():

@@ -180,6 +180,28 @@ def cpu_run(cfg, mode, n_per_step, steps, warmup, threads):
     return n_per_step * steps / dt, dt / steps * 1e3
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The driver parses stdout as ONE JSON line: libraries that write to fd 1 (NCCL prints its version there) are
+    redirected to stderr; emit() writes the result line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,6 +216,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warmup-seconds", type=float, default=2.0, help="minimum warm-up wall time (clock ramp)")
     args = ap.parse_args()
+    guard_stdout()
 
     from differentiable_tube_mpc_b200 import default_dubins_config
 
@@ -224,7 +247,7 @@ def main():
                                            "Python/PyTorch path measured 0.15-0.28 solves/s per core (BASELINE.md)"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ---------------- B200 arm ----------------
@@ -367,7 +390,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "nonfinite_instances": n_bad}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -185,11 +185,13 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
             lu2_solve(F, Qux03, Qux13, K03, K13);
             lu2_solve(F, tQu0, tQu1, k0, k1);
         } else if (!a0) {
-            K00 = Qux00 / A00; K01 = Qux01 / A00; K02 = Qux02 / A00; K03 = Qux03 / A00;
-            k0 = tQu0 / A00;
+            const R inv = R(1) / A00;
+            K00 = Qux00 * inv; K01 = Qux01 * inv; K02 = Qux02 * inv; K03 = Qux03 * inv;
+            k0 = tQu0 * inv;
         } else if (!a1) {
-            K10 = Qux10 / A11; K11 = Qux11 / A11; K12 = Qux12 / A11; K13 = Qux13 / A11;
-            k1 = tQu1 / A11;
+            const R inv = R(1) / A11;
+            K10 = Qux10 * inv; K11 = Qux11 * inv; K12 = Qux12 * inv; K13 = Qux13 * inv;
+            k1 = tQu1 * inv;
         }
         K00 = -K00; K01 = -K01; K02 = -K02; K03 = -K03;
         K10 = -K10; K11 = -K11; K12 = -K12; K13 = -K13;

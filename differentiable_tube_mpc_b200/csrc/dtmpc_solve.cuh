@@ -459,18 +459,28 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
     const R *Gk = GK + 8LL * T * S;
     State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
     R X0 = x.px, X1 = x.py, X2 = x.th, X3 = x.b;
-    for (int k = 0; k < T; ++k) {
-        const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
+    // inputs of step k+1 are fetched while step k computes (this sweep is the latency floor of an iteration)
+    struct In {
+        R v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1, N0, N1, N2, N3;
+    };
+    auto load_step = [&](int k, In &q) {
+        q.v0 = V[(2LL * k) * S]; q.v1 = V[(2LL * k + 1) * S];
         const R *o = GK + (8LL * k) * S;
-        const R K00 = o[0 * S], K01 = o[1 * S], K02 = o[2 * S], K03 = o[3 * S];
-        const R K10 = o[4 * S], K11 = o[5 * S], K12 = o[6 * S], K13 = o[7 * S];
-        const R k0 = Gk[(2LL * k) * S], k1 = Gk[(2LL * k + 1) * S];
-        const R N0 = X[(4LL * (k + 1) + 0) * S], N1 = X[(4LL * (k + 1) + 1) * S], N2 = X[(4LL * (k + 1) + 2) * S],
-                N3 = X[(4LL * (k + 1) + 3) * S];
+        q.K00 = o[0 * S]; q.K01 = o[1 * S]; q.K02 = o[2 * S]; q.K03 = o[3 * S];
+        q.K10 = o[4 * S]; q.K11 = o[5 * S]; q.K12 = o[6 * S]; q.K13 = o[7 * S];
+        q.k0 = Gk[(2LL * k) * S]; q.k1 = Gk[(2LL * k + 1) * S];
+        q.N0 = X[(4LL * (k + 1) + 0) * S]; q.N1 = X[(4LL * (k + 1) + 1) * S];
+        q.N2 = X[(4LL * (k + 1) + 2) * S]; q.N3 = X[(4LL * (k + 1) + 3) * S];
+    };
+    In in;
+    load_step(0, in);
+    for (int k = 0; k < T; ++k) {
+        In nx;
+        load_step(k + 1 < T ? k + 1 : k, nx);  // rows k+2 are not written before step k+1: safe to read ahead
         const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
-        const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
-        const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-        R u0 = m::fma_(al, du0, v0), u1 = m::fma_(al, du1, v1);
+        const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
+        const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
+        R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
         clamp_u(E, u0, u1);
         V[(2LL * k) * S] = u0;
         V[(2LL * k + 1) * S] = u1;
@@ -479,7 +489,8 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
         X[(4LL * (k + 1) + 1) * S] = x.py;
         X[(4LL * (k + 1) + 2) * S] = x.th;
         X[(4LL * (k + 1) + 3) * S] = x.b;
-        X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+        X0 = in.N0; X1 = in.N1; X2 = in.N2; X3 = in.N3;
+        in = nx;
     }
 }
 

@@ -308,6 +308,8 @@ def _apply_instance(cfg, inst, mode):
         cfg["system"]["horizon_N"] = int(inst["T"])
     if "dbas" in inst:
         cfg["dbas"].update(inst["dbas"])
+    if inst.get("fp32"):
+        cfg["use_float64"] = False   # the reference's float32 mode (core/tube_mpc.py:51, 675)
     if mode == "full":
         cfg["adaptation"]["adapt_nominal"] = True
     return cfg
@@ -408,6 +410,72 @@ def primitives_golden():
     return out
 
 
+def nominal_wrap_golden(workers):
+    """run_nominal.py `run_nominal_receding` (angle-wrapped heading error, warm start v = v_max, reg = ilqr_reg;
+    run_nominal.py:204-391) from seeded start states, 2 receding-horizon steps each.  The start state
+    (run_nominal.py:266) is made overridable in memory and ilqr_solve is the instrumented one."""
+    _, _, cfg = load_instrumented()
+    rng = np.random.default_rng(909)
+    insts = []
+    for inst in random_instances(14, 4711, cfg, h_min=0.5):
+        x0 = list(inst["_xbar0"])
+        x0[2] = float(rng.uniform(-2.0 * math.pi, 2.0 * math.pi))   # heading errors beyond +-pi exercise the wrap
+        insts.append(x0)
+    with ProcessPoolExecutor(workers) as ex:
+        res = list(ex.map(_nominal_job, insts))
+    out = {k: np.stack([r[k] for r in res]) for k in res[0]}
+    out["mode"] = np.array("nominal_wrap")
+    return out
+
+
+def _nominal_job(x0):
+    import contextlib
+    import io
+    import torch
+
+    tm_i, REC, cfg = load_instrumented()
+    for v in REC.values():
+        del v[:]
+    ddp = importlib.import_module(f"{PKG}.core.ddp")
+    ddp_i = sys.modules[f"{PKG}.core._ddp_instrumented"]
+    rn = importlib.import_module(f"{PKG}.run_nominal")
+    src = open(rn.__file__, encoding="utf-8").read()
+    src = _replace_once(src, "    x = torch.tensor([0.0, 0.0, float(np.pi / 4)], device=device, dtype=dtype)\n",
+                        "    x = torch.tensor(cfg['_x0'], device=device, dtype=dtype)\n")
+    mod = types.ModuleType(f"{PKG}._run_nominal_instrumented")
+    mod.__package__ = PKG
+    sys.modules[mod.__name__] = mod
+    exec(compile(src, "<run_nominal instrumented>", "exec"), mod.__dict__)
+    calls = []
+
+    def rec_ilqr(**kw):
+        n0 = len(REC["trace"])
+        X, V = ddp_i.ilqr_solve(**kw)
+        calls.append(dict(x0=kw["x0"].detach().clone(), V_init=kw["V_init"].detach().clone(), X=X.detach().clone(),
+                          V=V.detach().clone(), trace=REC["trace"][n0:], max_iter=kw["cfg"].max_iter,
+                          theta=torch.zeros(12, dtype=torch.float64),
+                          cfgv=torch.tensor([kw["cfg"].tol, kw["cfg"].reg] + list(kw["cfg"].line_search_alphas),
+                                            dtype=torch.float64)))
+        return X, V
+
+    orig = ddp.ilqr_solve
+    ddp.ilqr_solve = rec_ilqr
+    try:
+        cfg = copy.deepcopy(cfg)
+        cfg["_x0"] = x0
+        cfg["system"]["task_horizon_H"] = 2
+        cfg["system"]["horizon_N"] = 30
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.run_nominal_receding(cfg, device=torch.device("cpu"), run_dir=os.path.join(RUNS, f"nominal_{os.getpid()}"))
+    finally:
+        ddp.ilqr_solve = orig
+    n_alpha = len(cfg["system"]["line_search_alphas"])
+    packed = [_pack_ilqr(c, n_alpha) for c in calls[:2]]
+    while len(packed) < 2:  # the run stopped early (success / collision): repeat the last solve to keep shapes
+        packed.append(packed[-1])
+    return {k: np.stack([p[k] for p in packed]) for k in packed[0]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workers", type=int, default=8)
@@ -425,6 +493,8 @@ def main():
         "random_paper": (random_instances(40, 2024, cfg) + random_instances(16, 77, cfg, vary_weights=True), "paper", 1),
         "random_full": (random_instances(16, 4242, cfg) + random_instances(8, 99, cfg, vary_weights=True), "full", 1),
         "paper_T20": ([dict(i, T=20) for i in random_instances(12, 31337, cfg, vary_weights=True, h_min=0.05)], "paper", 2),
+        "random_paper_f32": ([dict(i, fp32=True) for i in random_instances(32, 2024, cfg, h_min=1.0)], "paper", 1),
+        "random_full_f32": ([dict(i, fp32=True) for i in random_instances(16, 4242, cfg, h_min=1.0)], "full", 1),
         "full_gamma": ([dict(i, T=20, dbas=dict(alpha=-1.0, gamma=g, nominal_tightening=-2.0))
                         for i, g in zip(random_instances(8, 555, cfg, h_min=0.02), (0.5, -0.5, 0.9, -0.9, 0.3, -0.3, 1.5, -1.5))],
                        "full", 2),
@@ -432,6 +502,9 @@ def main():
     if not args.only or args.only == "primitives":
         np.savez_compressed(os.path.join(GOLDEN, "primitives.npz"), **primitives_golden())
         print("wrote primitives.npz", flush=True)
+    if not args.only or args.only == "nominal_wrap":
+        np.savez_compressed(os.path.join(GOLDEN, "nominal_wrap.npz"), **nominal_wrap_golden(args.workers))
+        print("wrote nominal_wrap.npz", flush=True)
     for name, (insts, mode, H) in sets.items():
         if args.only and args.only != name:
             continue

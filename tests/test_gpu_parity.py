@@ -420,3 +420,27 @@ def test_edge_cases():
     with pytest.raises(ValueError):
         ops.ilqr_solve_batched(prob.system, prob.nominal, torch.zeros(2, 4, dtype=torch.float64, device=DEV),
                                torch.zeros(2, 7, 2, dtype=torch.float64, device=DEV), th)
+
+
+def test_run_nominal_angle_wrapped_variant_against_reference():
+    """BASELINE config #2 problem (run_nominal.py semantics: wrapped heading error, reg = ilqr_reg) vs the reference."""
+    from dataclasses import replace
+    from differentiable_tube_mpc_b200 import ops
+
+    g = load_golden("nominal_wrap")
+    cfg, prob = problem("paper", T=30)
+    ocp = replace(prob.nominal, angle_wrap=True, ilqr=replace(prob.nominal.ilqr, reg=float(cfg["system"]["ilqr_reg"])))
+    n = g["X"].shape[0]
+    flat = lambda k: g[k].reshape((2 * n,) + g[k].shape[2:])
+    r = ops.ilqr_solve_batched(prob.system, ocp, cu(flat("x0")), cu(flat("V_init")), cu(prob.theta_nom0), gains=True,
+                               trace=True)
+    assert int(r.status.sum()) == 0
+    it_w, it_g = flat("iters"), r.iters.cpu().numpy()
+    ai_w, ai_g = flat("alpha_idx"), r.alpha_idx.cpu().numpy()
+    good = np.array([it_w[i] == it_g[i] and np.array_equal(ai_w[i][: it_w[i]], ai_g[i][: it_g[i]]) for i in range(2 * n)])
+    assert good.mean() > 0.7
+    tame = np.nanmax(flat("best"), axis=1) < 1e12   # a start inside an obstacle (cost ~1e21) has chaotic gains
+    for key, got in (("X", r.X), ("V", r.V), ("K", r.K)):
+        e = per_instance_rel(got.cpu().numpy(), flat(key))
+        sel = good & tame if key == "K" else good
+        assert e[sel].max() < 1e-9, (key, e[sel].max())

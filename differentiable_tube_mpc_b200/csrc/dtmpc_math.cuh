@@ -158,6 +158,7 @@ template <typename R> struct Theta {
     R Q0, Q1, Q2, R0, R1, Qf0, Qf1, Qf2, qb, alpha, gamma, tight;
     // a = max(alpha, eps) for the dynamics (eps_dyn) and for the jacobian/gradients (eps_jac)
     R a_dyn, a_jac, jac_off;
+    R c1_dyn, c2_dyn, c3_dyn;  // 1/a, 1/a^2, 1/a^3 of the relaxed branch (a = a_dyn)
     // per-OCP numerical settings, kept with the lane so that lanes of one warp may work on
     // different OCPs (nominal / auxiliary) without divergent constant-bank reads
     R eps_dyn, eps_jac;
@@ -176,6 +177,9 @@ __device__ __forceinline__ void load_theta(Theta<R> &t, const R *__restrict__ p,
     t.a_dyn = M<R>::max_(t.alpha, o.eps_dyn);  // core/barrier.py:49
     t.a_jac = M<R>::max_(t.alpha, o.eps_jac);
     t.jac_off = o.tight_in_jac ? t.tight : R(0);
+    t.c1_dyn = R(1) / t.a_dyn;
+    t.c2_dyn = R(1) / (t.a_dyn * t.a_dyn);
+    t.c3_dyn = R(1) / (t.a_dyn * t.a_dyn * t.a_dyn);
 }
 
 // ---------------------------------------------------------------------------
@@ -322,9 +326,99 @@ template <typename R> __device__ __forceinline__ R wrap_angle(R err) {
     return M<R>::atan2_(s, c);
 }
 
-// Augmented state carried along a rollout: (px, py, th, b) plus B(h_bar(x)) of the
-// CURRENT state, which the next DBaS step needs as B_curr (core/barrier.py:94-98);
-// h(x_{k+1}) of step k is h(x_k) of step k+1, so it is evaluated once.
+// h (value only) at NC points at once.  The obstacle loop is shared, so the NC evaluations form one instruction
+// stream the scheduler can interleave (the line search rolls NC candidates per thread for instruction-level
+// parallelism: a lone fp64 dependency chain issues once per ~9 cycles).  Per point the arithmetic is exactly that of
+// eval_h<R, false>; every rollout in the library goes through this function, so results are bit-identical wherever a
+// state is propagated (initial rollout, candidates, commit, plant step).
+template <typename R, int NC>
+__device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC], const R (&py)[NC], R (&h)[NC]) {
+    using m = M<R>;
+    const int n = e.n_obs;
+    if (n == 0) {
+#pragma unroll
+        for (int q = 0; q < NC; ++q) h[q] = R(1);
+        return;
+    }
+    if (e.agg == DTMPC_AGG_SINGLE) {
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const R dx = px[q] - e.cx[0], dy = py[q] - e.cy[0];
+            h[q] = m::fma_(dy, dy, dx * dx) - e.r2[0];
+        }
+        return;
+    }
+    if (e.agg == DTMPC_AGG_MIN) {
+        R best[NC];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) best[q] = m::inf_();
+        for (int i = 0; i < n; ++i) {
+            const R cx = e.cx[i], cy = e.cy[i], r2 = e.r2[i];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                const R dx = px[q] - cx, dy = py[q] - cy;
+                const R hi = m::fma_(dy, dy, dx * dx) - r2;
+                if (hi < best[q] || i == 0) best[q] = hi;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NC; ++q) h[q] = best[q];
+        return;
+    }
+    R z1[NC], z2[NC], z3[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) z1[q] = z2[q] = z3[q] = -m::inf_();
+    for (int i = 0; i < n; ++i) {
+        const R cx = e.cx[i], cy = e.cy[i], r2 = e.r2[i];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const R dx = px[q] - cx, dy = py[q] - cy;
+            const R hi = m::fma_(dy, dy, dx * dx) - r2;
+            const R z = e.nbeta * hi;
+            const bool p1 = z > z1[q], p2 = z > z2[q], p3 = z > z3[q];
+            z3[q] = p2 ? z2[q] : (p3 ? z : z3[q]);
+            z2[q] = p1 ? z1[q] : (p2 ? z : z2[q]);
+            z1[q] = p1 ? z : z1[q];
+        }
+    }
+    const R reach = sizeof(R) == 8 ? R(-40) : R(-18);
+    R s[NC];
+    bool far = false;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        s[q] = R(1) + m::exp_(z2[q] - z1[q]);  // exp(-inf) = 0 for a single obstacle
+        far |= (z3[q] - z1[q] > reach);
+    }
+    if (far) {  // three or more obstacles within reach of one of the points: the reference's full ordered sum (rare)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            if (z3[q] - z1[q] > reach) {
+                R acc = R(0);
+                for (int i = 0; i < n; ++i) {
+                    const R dx = px[q] - e.cx[i], dy = py[q] - e.cy[i];
+                    const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+                    acc += m::exp_(e.nbeta * hi - z1[q]);
+                }
+                s[q] = acc;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NC; ++q) h[q] = e.ninv_beta * (z1[q] + m::log_(s[q]));
+}
+
+// Relaxed inverse barrier of the dynamics (core/barrier.py:36-59) without a data-dependent branch: the relaxed
+// polynomial 1/a - d/a^2 + d^2/a^3 uses the per-instance reciprocals precomputed in Theta.
+template <typename R> __device__ __forceinline__ R barrier_B_dyn(const Theta<R> &t, R z) {
+    using m = M<R>;
+    const R safe = R(1) / m::max_(z, t.eps_dyn);
+    const R d = z - t.a_dyn;
+    const R relaxed = m::fma_(d * d, t.c3_dyn, m::fma_(-d, t.c2_dyn, t.c1_dyn));
+    return z >= t.a_dyn ? safe : relaxed;
+}
+
+// Augmented state carried along a rollout: (px, py, th, b) plus B(h_bar(x)) of the CURRENT state, which the next
+// DBaS step needs as B_curr (core/barrier.py:94-98); h(x_{k+1}) of step k is h(x_k) of step k+1, so it is evaluated once.
 template <typename R> struct State {
     R px, py, th, b, Bc;
 };
@@ -332,31 +426,46 @@ template <typename R> struct State {
 // B_curr for a state that did not come out of step() (the initial state).
 template <typename R>
 __device__ __forceinline__ R barrier_of_state(const EnvT<R> &e, const Theta<R> &t, R px, R py) {
-    R h, gx, gy;
-    eval_h<R, false>(e, px, py, h, gx, gy);
-    return barrier_B(h - t.tight, t.a_dyn, t.eps_dyn);
+    R pxa[1] = {px}, pya[1] = {py}, h[1];
+    eval_h_multi<R, 1>(e, pxa, pya, h);
+    return barrier_B_dyn(t, h[0] - t.tight);
 }
 
-// One step of f_hat: dubins_step (core/systems/dubins.py:36-42) + dbas_step (core/barrier.py:93-108).
+// One step of f_hat for NC states: dubins_step (core/systems/dubins.py:36-42) + dbas_step (core/barrier.py:93-108).
+template <typename R, int NC>
+__device__ __forceinline__ void step_multi(const EnvT<R> &e, const Theta<R> &t, State<R> (&x)[NC], const R (&u0)[NC],
+                                           const R (&u1)[NC]) {
+    using m = M<R>;
+    R pxn[NC], pyn[NC], thn[NC], h[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        R s, c;
+        m::sincos_(x[q].th, &s, &c);
+        const R dtv = e.dt * u0[q];
+        pxn[q] = m::fma_(dtv, c, x[q].px);
+        pyn[q] = m::fma_(dtv, s, x[q].py);
+        thn[q] = m::fma_(e.dt, u1[q], x[q].th);
+    }
+    eval_h_multi<R, NC>(e, pxn, pyn, h);
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        const R Bn = barrier_B_dyn(t, h[q] - t.tight);
+        // b+ = B_next - gamma * (B_curr - b)
+        const R bn = m::fma_(-t.gamma, x[q].Bc - x[q].b, Bn);
+        x[q].px = pxn[q];
+        x[q].py = pyn[q];
+        x[q].th = thn[q];
+        x[q].b = bn;
+        x[q].Bc = Bn;
+    }
+}
+
 template <typename R>
 __device__ __forceinline__ void step(const EnvT<R> &e, const Theta<R> &t, State<R> &x, R u0, R u1) {
-    using m = M<R>;
-    R s, c;
-    m::sincos_(x.th, &s, &c);
-    R dtv = e.dt * u0;
-    R pxn = m::fma_(dtv, c, x.px);
-    R pyn = m::fma_(dtv, s, x.py);
-    R thn = m::fma_(e.dt, u1, x.th);
-    R h, gx, gy;
-    eval_h<R, false>(e, pxn, pyn, h, gx, gy);
-    R Bn = barrier_B(h - t.tight, t.a_dyn, t.eps_dyn);
-    // b+ = B_next - gamma * (B_curr - b)
-    R bn = m::fma_(-t.gamma, x.Bc - x.b, Bn);
-    x.px = pxn;
-    x.py = pyn;
-    x.th = thn;
-    x.b = bn;
-    x.Bc = Bn;
+    State<R> xs[1] = {x};
+    const R a0[1] = {u0}, a1[1] = {u1};
+    step_multi<R, 1>(e, t, xs, a0, a1);
+    x = xs[0];
 }
 
 // Stage cost  sum Q dx^2 + sum R du^2 + q_b b^2   (core/tube_mpc.py:823-827, 875-880; 281-286, 358-364)

@@ -338,27 +338,34 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward line search (core/ddp.py:256-290): blockDim = (32, n_eval); warp y rolls out candidate y for the 32
-// instances of the CTA, so the CTA touches each gain / trajectory row once for all candidates.
+// forward line search (core/ddp.py:256-290).  blockDim = (32, ceil(n_eval / NC)): a CTA covers 32 instances; thread
+// (lane, g) rolls out candidates g*NC .. g*NC+NC-1 of its instance in lockstep.  NC independent dependency chains per
+// thread give the instruction-level parallelism a single fp64 chain lacks (DFMA latency 8.75 cycles, tools/micro), and
+// the gains / trajectory rows of a step are loaded once per thread for its NC candidates.  Only costs leave the kernel.
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef DTMPC_FWD_PREFETCH
-#define DTMPC_FWD_PREFETCH 2
-#endif
 #ifndef DTMPC_FWD_MAXNREG
 #define DTMPC_FWD_MAXNREG 104
 #endif
-template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
+template <typename R, int NC>
+__global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * 32 + threadIdx.x;
     if (j >= n_act) return;
-    const int c = threadIdx.y;
     const long long i = P.ws.list[P.parity][j];
     const long long S = P.B;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
-    const int a_idx = P.eval_idx[c];
-    const R al = P.ocp.alphas[a_idx];
+    int a_idx[NC];
+    R al[NC];
+    bool valid[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        const int c = threadIdx.y * NC + q;
+        valid[q] = c < P.n_eval;
+        a_idx[q] = P.eval_idx[valid[q] ? c : P.n_eval - 1];  // a padded slot repeats the last candidate
+        al[q] = P.ocp.alphas[a_idx[q]];
+    }
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
     R t0 = R(0), t1 = R(0), t2 = R(0);
@@ -371,79 +378,49 @@ template <typename R> __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(
     const R *GK = P.ws.gains + i;
     const R *Gk = GK + 8LL * T * S;
 
-    State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
-    R J = R(0);
-    // Inputs of one step; the next step's inputs are fetched while the current step computes (register double
-    // buffering): the loads do not depend on the rollout, and a step is ~2k issue cycles, so one step of lookahead
-    // covers the DRAM latency that otherwise stalls every warp at the top of each step.
-    struct StepIn {
-        R X0, X1, X2, X3, v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1;
-        RefPt<R> r;
-    };
-    auto load_step = [&](int k, StepIn &q) {
-        q.X0 = X[(4LL * k + 0) * S]; q.X1 = X[(4LL * k + 1) * S]; q.X2 = X[(4LL * k + 2) * S]; q.X3 = X[(4LL * k + 3) * S];
-        q.v0 = V[(2LL * k) * S]; q.v1 = V[(2LL * k + 1) * S];
-        const R *o = GK + (8LL * k) * S;
-        q.K00 = o[0 * S]; q.K01 = o[1 * S]; q.K02 = o[2 * S]; q.K03 = o[3 * S];
-        q.K10 = o[4 * S]; q.K11 = o[5 * S]; q.K12 = o[6 * S]; q.K13 = o[7 * S];
-        q.k0 = Gk[(2LL * k) * S]; q.k1 = Gk[(2LL * k + 1) * S];
-        ref_at(P, i, k, true, t0, t1, t2, q.r);
-    };
-#if DTMPC_FWD_PREFETCH == 1
-    // L1 prefetch hints two steps ahead, one row per warp in turn: the 6 candidate warps of the CTA read the same rows
-    auto prefetch_step = [&](int k) {
-        if (k >= T) return;
-        const int ne = blockDim.y;
-        for (int r = c; r < 21; r += ne) {
-            const R *p;
-            if (r < 4) p = X + (4LL * k + r) * S;
-            else if (r < 6) p = V + (2LL * k + (r - 4)) * S;
-            else if (r < 14) p = GK + (8LL * k + (r - 6)) * S;
-            else if (r < 16) p = Gk + (2LL * k + (r - 14)) * S;
-            else if (!P.use_ref) break;
-            else if (r < 19) p = P.ws.ref + (3LL * k + (r - 16)) * S + i;
-            else p = P.ws.ref + (3LL * (T + 1) + 2LL * k + (r - 19)) * S + i;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    State<R> x[NC];
+    R J[NC];
+    {
+        const State<R> x0{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            x[q] = x0;
+            J[q] = R(0);
         }
-    };
-    prefetch_step(1);
-    StepIn in;
+    }
     for (int k = 0; k < T; ++k) {
-        prefetch_step(k + 2);
-        load_step(k, in);
-        StepIn nx;
-#elif DTMPC_FWD_PREFETCH == 2
-    StepIn in;
-    for (int k = 0; k < T; ++k) {
-        load_step(k, in);
-        StepIn nx;
-#else
-    StepIn in;
-    load_step(0, in);
-    for (int k = 0; k < T; ++k) {
-        StepIn nx;
-        load_step(k + 1 < T ? k + 1 : k, nx);
-#endif
-        // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
-        const R d0 = x.px - in.X0, d1 = x.py - in.X1, d2 = x.th - in.X2, d3 = x.b - in.X3;
-        const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
-        const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
-        R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
-        clamp_u(E, u0, u1);
-        J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, in.r.x0, in.r.x1, in.r.x2, in.r.u0, in.r.u1);
-        step(E, th, x, u0, u1);
-#if DTMPC_FWD_PREFETCH == 0
-        in = nx;
-#else
-        (void)nx;
-#endif
+        const R X0 = X[(4LL * k + 0) * S], X1 = X[(4LL * k + 1) * S], X2 = X[(4LL * k + 2) * S], X3 = X[(4LL * k + 3) * S];
+        const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
+        const R *o = GK + (8LL * k) * S;
+        const R K00 = o[0 * S], K01 = o[1 * S], K02 = o[2 * S], K03 = o[3 * S];
+        const R K10 = o[4 * S], K11 = o[5 * S], K12 = o[6 * S], K13 = o[7 * S];
+        const R k0 = Gk[(2LL * k) * S], k1 = Gk[(2LL * k + 1) * S];
+        RefPt<R> r;
+        ref_at(P, i, k, true, t0, t1, t2, r);
+        R u0[NC], u1[NC];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
+            const R d0 = x[q].px - X0, d1 = x[q].py - X1, d2 = x[q].th - X2, d3 = x[q].b - X3;
+            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
+            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
+            u0[q] = m::fma_(al[q], du0, v0);
+            u1[q] = m::fma_(al[q], du1, v1);
+            clamp_u(E, u0[q], u1[q]);
+            J[q] += stage_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, u0[q], u1[q], r.x0, r.x1, r.x2, r.u0, r.u1);
+        }
+        step_multi<R, NC>(E, th, x, u0, u1);
     }
     RefPt<R> r;
     ref_at(P, i, T, false, t0, t1, t2, r);
-    J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
-    P.ws.J[(long long)a_idx * S + i] = J;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        J[q] += terminal_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, r.x0, r.x1, r.x2);
+        if (valid[q]) P.ws.J[(long long)a_idx[q] * S + i] = J[q];
+    }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
 // Rolls the accepted candidate out once more and overwrites the instance's trajectory in place (X_k of the old
 // trajectory is read before x_{k+1} of the new one lands in the next row).
 template <typename R> __device__ __forceinline__ void commit_candidate(const SolveParams<R> &P, long long i, R al) {

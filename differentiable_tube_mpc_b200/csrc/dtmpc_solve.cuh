@@ -344,10 +344,10 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
 // the gains / trajectory rows of a step are loaded once per thread for its NC candidates.  Only costs leave the kernel.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef DTMPC_FWD_MAXNREG
-#define DTMPC_FWD_MAXNREG 104
+#define DTMPC_FWD_MAXNREG 168
 #endif
 template <typename R, int NC>
-__global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
+__global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * 32 + threadIdx.x;

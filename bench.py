@@ -142,6 +142,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
+def traffic_from_profile():
+    """DRAM bytes (read + write) per launch of the largest kernel, from the committed ncu --set full capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return {"kernel": t["kernel"], "bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -372,7 +381,7 @@ def main():
                     "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64 if peak64 > 0 else None,
                     "peak_source": "DFMA loop measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                     "flop_model": "SURVEY 8d dense reference form x actual iterations; exp=25 log=30 sincos=50 flop-eq",
-                    "kernel_ms": kern_ms, "iters_per_solve": iters_total / B, "traffic": None,
+                    "kernel_ms": kern_ms, "iters_per_solve": iters_total / B, "traffic": traffic_from_profile(),
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                             "bytes_per_solve": bytes_solve}}

@@ -295,3 +295,36 @@ def test_fp32_mode_against_the_reference_float32_run(name):
         assert np.median(e) < 1e-3, (key, np.median(e))
     assert rel_err(sa.loss.double().cpu().numpy(), g["loss"][:, 0] if "loss" in g.files else
                    ((g["aux_X"][:, 0, :, :3] - g["nom_X"][:, 0, :, :3]) ** 2).sum((1, 2)) + (g["aux_X"][:, 0, :, 3] ** 2).sum(1)) < 1e-5
+
+
+def test_device_closed_loop_batch():
+    """closed_loop.ClosedLoop: B tubes for H steps on the device (plant step, DBaS propagation, warm-start shift,
+    Algorithm-2 update) with device-side logs.  With the learning rate at 0 the tubes are independent, so a tube's
+    trajectory must not depend on the batch it runs in (bitwise)."""
+    from differentiable_tube_mpc_b200 import default_dubins_config
+    from differentiable_tube_mpc_b200.closed_loop import ClosedLoop
+
+    cfg = default_dubins_config()
+    cfg["system"]["horizon_N"] = 20
+    cfg["adaptation"]["lr_eta"] = 0.0
+    H = 4
+    w = torch.rand(H, 256, 3, dtype=torch.float64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)) * 0.1 - 0.05
+    x0 = cu(make_instances(256, 9, cfg)[0])
+    runs = {}
+    for B in (256, 64):
+        loop = ClosedLoop(cfg, device=DEV, batch=B, n_log=64, x0=x0[:B], disturbance_fn=lambda t, B=B: w[t, :B].contiguous())
+        runs[B] = loop.run(H)
+        assert runs[B]["x_real"].shape == (H, 64, 3) and runs[B]["loss"].shape == (H, 64) and runs[B]["Qa"].shape == (H, 3)
+    for k in ("x_real", "u_real", "x_bar", "b_real", "loss"):
+        assert torch.equal(runs[256][k], runs[64][k]), k
+    # default device disturbance + adaptation on: runs, stays finite, parameters move, reproducible from the seed
+    cfg["adaptation"]["lr_eta"] = 0.05
+    a = ClosedLoop(cfg, device=DEV, batch=128, n_log=2).run(3)
+    b = ClosedLoop(cfg, device=DEV, batch=128, n_log=2).run(3)
+    assert torch.equal(a["x_real"], b["x_real"]) and bool(torch.isfinite(a["loss"]).all())
+    assert not torch.equal(a["Qa"][0], a["Qa"][-1])
+    # a non-finite start state is reported when the run is checked, not silently carried
+    bad = x0[:8].clone()
+    bad[3, 0] = float("nan")
+    with pytest.raises(FloatingPointError):
+        ClosedLoop(cfg, device=DEV, batch=8, x0=bad).run(2)

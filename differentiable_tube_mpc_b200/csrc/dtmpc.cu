@@ -109,14 +109,14 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
     char *J = take(nB * sizeof(R) * (size_t)n_alpha);
     char *traj = take(nB * sizeof(R) * (size_t)traj_rows(T));
     char *gains = take(nB * sizeof(R) * 10 * (size_t)T);
-    char *lin = take(nB * sizeof(R) * 8 * (size_t)T);
+    char *g = take(nB * sizeof(R) * 2 * (size_t)(T + 1));
     char *ref = take(nB * sizeof(R) * (size_t)ref_rows(T));
     if (w) {
         w->counts = (int *)counts;
         w->list[0] = (int *)l0; w->list[1] = (int *)l1;
         w->it = (int *)it; w->flags = (int *)flags;
         w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0; w->J = (R *)J;
-        w->traj = (R *)traj; w->gains = (R *)gains; w->lin = (R *)lin; w->ref = (R *)ref;
+        w->traj = (R *)traj; w->gains = (R *)gains; w->g = (R *)g; w->ref = (R *)ref;
     }
     return off;
 }
@@ -155,10 +155,8 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
         if (P.ocp.alphas[c] != R(0)) P.eval_idx[P.n_eval++] = c;
     P.parity = 0;
     init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
-    const unsigned gLin = (unsigned)((B * T + 255) / 256);
     const unsigned gFwd = (unsigned)((B + 31) / 32);
     for (int it = 0; it < P.ocp.max_iter; ++it) {
-        lin_kernel<R><<<gLin, 256, 0, st>>>(P);
         ric_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
         if (P.n_eval > 0) {
             const int nc = fwd_candidates_per_thread(P.n_eval);

@@ -519,6 +519,36 @@ __device__ __forceinline__ void step_multi(const EnvT<R> &e, const Theta<R> &t, 
     }
 }
 
+// barrier_dB is defined below (jacobian section)
+template <typename R> __device__ __forceinline__ R barrier_dB(R z, R a, R eps);
+template <typename R, bool GRAD> __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx, R &gy);
+
+// step() that also returns g = B'(h_jac(x+)) grad h(x+), the quantity the barrier row of the augmented jacobian is
+// built from (core/systems/dubins_aug_jac.py:95-129).  The state update is bit-identical to step(): h comes out of
+// the same operation sequence in eval_h<R, true> and eval_h_multi.
+template <typename R>
+__device__ __forceinline__ void step_g(const EnvT<R> &e, const Theta<R> &t, State<R> &x, R u0, R u1, R &gx, R &gy) {
+    using m = M<R>;
+    R s, c;
+    m::sincos_(x.th, &s, &c);
+    const R dtv = e.dt * u0;
+    const R pxn = m::fma_(dtv, c, x.px);
+    const R pyn = m::fma_(dtv, s, x.py);
+    const R thn = m::fma_(e.dt, u1, x.th);
+    R h, hx, hy;
+    eval_h<R, true>(e, pxn, pyn, h, hx, hy);
+    const R Bn = barrier_B_dyn(t, h - t.tight);
+    const R dB = barrier_dB(h - t.jac_off, t.a_jac, t.eps_jac);
+    gx = dB * hx;
+    gy = dB * hy;
+    const R bn = m::fma_(-t.gamma, x.Bc - x.b, Bn);
+    x.px = pxn;
+    x.py = pyn;
+    x.th = thn;
+    x.b = bn;
+    x.Bc = Bn;
+}
+
 template <typename R>
 __device__ __forceinline__ void step(const EnvT<R> &e, const Theta<R> &t, State<R> &x, R u0, R u1) {
     State<R> xs[1] = {x};

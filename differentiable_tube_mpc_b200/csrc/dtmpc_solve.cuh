@@ -4,9 +4,8 @@
 // kernel is FP64-pipe bound, not HBM bound.  Every iLQR iteration of the whole batch is four launches over the list
 // of still-active instances:
 //
-//   lin_kernel   thread per (instance, k)          linearisation: sincos, h, grad h, B' -> 8 jacobian entries
-//                                                  (embarrassingly parallel in k: taken off the serial chain)
-//   ric_kernel   thread per instance               backward Riccati sweep, register-resident V_x / V_xx, gains K, k
+//   ric_kernel   thread per instance               linearisation (from the stored barrier gradients g_k) + backward
+//                                                  Riccati sweep, register-resident V_x / V_xx, gains K, k
 //   fwd_kernel   thread per (instance, candidate)  forward line search: every alpha != 0 rolls out in its own lane,
 //                                                  one warp per candidate, 32 instances per CTA, so the gains and the
 //                                                  current trajectory are fetched once per CTA (L1) for all candidates;
@@ -44,7 +43,9 @@ template <typename R> struct SolveWs {
     R *J;            // [n_alpha][B] candidate costs
     R *traj;         // [4(T+1)+2T][B] current trajectory X, V
     R *gains;        // [10T][B]  K (8 rows per k) then k (2 rows per k)
-    R *lin;          // [8T][B]
+    R *g;            // [2(T+1)][B] g_k = B'(h(x_k)) grad h(x_k): what the barrier row of the jacobian needs. Written by
+                     // whoever rolls the trajectory out (init, commit); a separate linearisation kernel and its 8 stored
+                     // jacobian entries per step made the backward pass HBM-bound (profiles/r01b)
     R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)
 };
 
@@ -131,6 +132,12 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     R *X = P.ws.traj + i;                       // buffer 0
     R *V = X + 4LL * (T + 1) * S;
     X[0 * S] = x.px; X[1 * S] = x.py; X[2 * S] = x.th; X[3 * S] = x.b;
+    R *G = P.ws.g + i;
+    {
+        R g0x, g0y, h0;
+        barrier_grad(E, th, x.px, x.py, g0x, g0y, h0);
+        G[0 * S] = g0x; G[1 * S] = g0y;
+    }
     const R *vp = P.io.V_init + i * (2LL * T);
     R J = R(0);
     for (int k = 0; k < T; ++k) {
@@ -141,11 +148,14 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
         RefPt<R> r;
         ref_at(P, i, k, true, t0, t1, t2, r);
         J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
-        step(E, th, x, u0, u1);
+        R gx, gy;
+        step_g(E, th, x, u0, u1, gx, gy);
         X[(4LL * (k + 1) + 0) * S] = x.px;
         X[(4LL * (k + 1) + 1) * S] = x.py;
         X[(4LL * (k + 1) + 2) * S] = x.th;
         X[(4LL * (k + 1) + 3) * S] = x.b;
+        G[(2LL * (k + 1) + 0) * S] = gx;
+        G[(2LL * (k + 1) + 1) * S] = gy;
     }
     RefPt<R> r;
     ref_at(P, i, T, false, t0, t1, t2, r);
@@ -159,41 +169,21 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// linearisation (core/ddp.py:172-199 -> core/systems/dubins_aug_jac.py:61-139), thread per (instance, k)
+// linearisation (core/ddp.py:172-199 -> core/systems/dubins_aug_jac.py:61-139) + backward Riccati sweep
+// (core/ddp.py:208-254), thread per instance
 // ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __launch_bounds__(256) lin_kernel(const __grid_constant__ SolveParams<R> P) {
-    const int n_act = P.ws.counts[P.parity];
-    const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (g == 0) P.ws.counts[P.parity ^ 1] = 0;  // the list sel_kernel will fill
-    const int T = P.ocp.T;
-    if (g >= (long long)n_act * T) return;
-    const int j = (int)(g % n_act), k = (int)(g / n_act);
-    const long long i = P.ws.list[P.parity][j];
-    const long long S = P.B;
-    const EnvT<R> &E = P.env;
-    Theta<R> th;
-    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
-    const R *X = P.ws.traj + i;
-    const R *V = X + 4LL * (T + 1) * S;
-    const R pth = X[(4LL * k + 2) * S];
-    const R v = V[(2LL * k) * S];
-    R gnx, gny, gcx = R(0), gcy = R(0), hv;
-    barrier_grad(E, th, X[(4LL * (k + 1) + 0) * S], X[(4LL * (k + 1) + 1) * S], gnx, gny, hv);
-    if (th.gamma != R(0)) barrier_grad(E, th, X[(4LL * k + 0) * S], X[(4LL * k + 1) * S], gcx, gcy, hv);
-    Lin<R> L;
-    linearize(E, th, pth, v, gnx, gny, gcx, gcy, L);
-    R *o = P.ws.lin + (8LL * k) * S + i;
-    o[0 * S] = L.a02; o[1 * S] = L.a12; o[2 * S] = L.r0; o[3 * S] = L.r1;
-    o[4 * S] = L.r2; o[5 * S] = L.b00; o[6 * S] = L.b10; o[7 * S] = L.s0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// backward Riccati sweep (core/ddp.py:208-254), thread per instance
-// ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(const __grid_constant__ SolveParams<R> P) {
+#ifndef DTMPC_RIC_MAXNREG
+#define DTMPC_RIC_MAXNREG 255
+#endif
+#ifndef DTMPC_RIC_PREFETCH
+#define DTMPC_RIC_PREFETCH 1
+#endif
+template <typename R>
+__global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
+    if (j == 0) P.ws.counts[P.parity ^ 1] = 0;  // the list sel_kernel will fill (first kernel of the iteration)
     if (j >= n_act) return;
     const long long i = P.ws.list[P.parity][j];
     const long long S = P.B;
@@ -208,7 +198,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
     }
     const R *X = P.ws.traj + i;
     const R *V = X + 4LL * (T + 1) * S;
-    const R *LN = P.ws.lin + i;
+    const R *G = P.ws.g + i;
     R *GK = P.ws.gains + i;
     R *Gk = GK + 8LL * T * S;
     const R reg = P.ocp.reg;
@@ -235,27 +225,33 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
     struct RicIn {
         R px, py, pt, pb, u0, u1;
         RefPt<R> r;
-        Lin<R> L;
+        R gx, gy;
     };
     auto load_step = [&](int k, RicIn &q) {
         q.px = X[(4LL * k + 0) * S]; q.py = X[(4LL * k + 1) * S]; q.pt = X[(4LL * k + 2) * S]; q.pb = X[(4LL * k + 3) * S];
         q.u0 = V[(2LL * k) * S]; q.u1 = V[(2LL * k + 1) * S];
         ref_at(P, i, k, true, t0, t1, t2, q.r);
-        const R *o = LN + (8LL * k) * S;
-        q.L.a02 = o[0 * S]; q.L.a12 = o[1 * S]; q.L.r0 = o[2 * S]; q.L.r1 = o[3 * S];
-        q.L.r2 = o[4 * S]; q.L.b00 = o[5 * S]; q.L.b10 = o[6 * S]; q.L.s0 = o[7 * S];
+        q.gx = G[(2LL * k + 0) * S]; q.gy = G[(2LL * k + 1) * S];
     };
+    R gnx = G[(2LL * T + 0) * S], gny = G[(2LL * T + 1) * S];  // g at x_T, then carried backwards
     RicIn in;
+#if DTMPC_RIC_PREFETCH
     load_step(T - 1, in);
+#endif
     for (int k = T - 1; k >= 0; --k) {
         RicIn nx;
+#if DTMPC_RIC_PREFETCH
         load_step(k > 0 ? k - 1 : 0, nx);
+#else
+        load_step(k, in);
+        nx = in;
+#endif
 #if DTMPC_L2_PREFETCH > 0
         if (k - 1 - DTMPC_L2_PREFETCH >= 0) {
             const int kp = k - 1 - DTMPC_L2_PREFETCH;
             for (int c = 0; c < 4; ++c) prefetch_l2(X + (4LL * kp + c) * S);
             for (int c = 0; c < 2; ++c) prefetch_l2(V + (2LL * kp + c) * S);
-            for (int c = 0; c < 8; ++c) prefetch_l2(LN + (8LL * kp + c) * S);
+            for (int c = 0; c < 2; ++c) prefetch_l2(G + (2LL * kp + c) * S);
             if (P.use_ref) {
                 for (int c = 0; c < 3; ++c) prefetch_l2(P.ws.ref + (3LL * kp + c) * S + i);
                 for (int c = 0; c < 2; ++c) prefetch_l2(P.ws.ref + (3LL * (T + 1) + 2LL * kp + c) * S + i);
@@ -264,7 +260,10 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) ric_kernel(con
 #endif
         const R px = in.px, py = in.py, pt = in.pt, pb = in.pb, u0 = in.u0, u1 = in.u1;
         const RefPt<R> r = in.r;
-        const Lin<R> L = in.L;
+        Lin<R> L;
+        linearize(E, th, pt, u0, gnx, gny, in.gx, in.gy, L);
+        gnx = in.gx;
+        gny = in.gy;
         in = nx;
         // stage derivatives, core/cost_derivs.py:58-76, 110-129
         const R lx0 = lxx0 * (px - r.x0), lx1 = lxx1 * (py - r.x1);
@@ -453,6 +452,7 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
     R *X = P.ws.traj + i;
     R *V = X + 4LL * (T + 1) * S;
+    R *G = P.ws.g + i;
     const R *GK = P.ws.gains + i;
     const R *Gk = GK + 8LL * T * S;
     State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
@@ -491,11 +491,14 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
         clamp_u(E, u0, u1);
         V[(2LL * k) * S] = u0;
         V[(2LL * k + 1) * S] = u1;
-        step(E, th, x, u0, u1);
+        R gx, gy;
+        step_g(E, th, x, u0, u1, gx, gy);
         X[(4LL * (k + 1) + 0) * S] = x.px;
         X[(4LL * (k + 1) + 1) * S] = x.py;
         X[(4LL * (k + 1) + 2) * S] = x.th;
         X[(4LL * (k + 1) + 3) * S] = x.b;
+        G[(2LL * (k + 1) + 0) * S] = gx;
+        G[(2LL * (k + 1) + 1) * S] = gy;
         X0 = in.N0; X1 = in.N1; X2 = in.N2; X3 = in.N3;
         in = nx;
     }

@@ -172,11 +172,13 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
 // linearisation (core/ddp.py:172-199 -> core/systems/dubins_aug_jac.py:61-139) + backward Riccati sweep
 // (core/ddp.py:208-254), thread per instance
 // ---------------------------------------------------------------------------------------------------------------
+// Both are HBM-bound streaming sweeps: occupancy beats a register double buffer.  Same-box A/B at B = 65,536, full
+// mode: 255 regs + read-ahead 26.0 ms, 128 regs + no read-ahead 25.0 ms per tube solve.
 #ifndef DTMPC_RIC_MAXNREG
-#define DTMPC_RIC_MAXNREG 255
+#define DTMPC_RIC_MAXNREG 128
 #endif
 #ifndef DTMPC_RIC_PREFETCH
-#define DTMPC_RIC_PREFETCH 1
+#define DTMPC_RIC_PREFETCH 0
 #endif
 template <typename R>
 __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant__ SolveParams<R> P) {
@@ -441,6 +443,13 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// commit sweep: read-ahead of one step under a 96-register cap measured best (25.65 vs 26.0 ms, same box)
+#ifndef DTMPC_SEL_PREFETCH
+#define DTMPC_SEL_PREFETCH 1
+#endif
+#ifndef DTMPC_SEL_MAXNREG
+#define DTMPC_SEL_MAXNREG 96
+#endif
 // Rolls the accepted candidate out once more and overwrites the instance's trajectory in place (X_k of the old
 // trajectory is read before x_{k+1} of the new one lands in the next row).
 template <typename R> __device__ __forceinline__ void commit_candidate(const SolveParams<R> &P, long long i, R al) {
@@ -471,10 +480,17 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
         q.N2 = X[(4LL * (k + 1) + 2) * S]; q.N3 = X[(4LL * (k + 1) + 3) * S];
     };
     In in;
+#if DTMPC_SEL_PREFETCH
     load_step(0, in);
+#endif
     for (int k = 0; k < T; ++k) {
         In nx;
+#if DTMPC_SEL_PREFETCH
         load_step(k + 1 < T ? k + 1 : k, nx);  // rows k+2 are not written before step k+1: safe to read ahead
+#else
+        load_step(k, in);
+        nx = in;
+#endif
 #if DTMPC_L2_PREFETCH > 0
         if (k + 1 + DTMPC_L2_PREFETCH < T) {
             const int kp = k + 1 + DTMPC_L2_PREFETCH;
@@ -507,7 +523,7 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
 // ---------------------------------------------------------------------------------------------------------------
 // selection (core/ddp.py:293-305): strict '<' in list order, tolerance break on the accepted costs, compaction
 // ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __launch_bounds__(LS_BLOCK) sel_kernel(const __grid_constant__ SolveParams<R> P) {
+template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) sel_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * LS_BLOCK + threadIdx.x;

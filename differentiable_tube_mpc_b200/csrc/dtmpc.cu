@@ -106,17 +106,18 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
     char *l0 = take(nB * sizeof(int)), *l1 = take(nB * sizeof(int));
     char *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
     char *Jcur = take(nB * sizeof(R)), *prev = take(nB * sizeof(R)), *B0 = take(nB * sizeof(R));
-    char *J = take(nB * sizeof(R) * (size_t)n_alpha);
-    char *traj = take(nB * sizeof(R) * (size_t)traj_rows(T));
+    (void)n_alpha;  // candidate costs never leave the line-search kernel
+    char *dec = take(nB * sizeof(int)), *keep = take((nB / 32 + 1) * sizeof(unsigned));
+    char *traj0 = take(nB * sizeof(R) * (size_t)traj_rows(T)), *traj1 = take(nB * sizeof(R) * (size_t)traj_rows(T));
     char *gains = take(nB * sizeof(R) * 10 * (size_t)T);
-    char *g = take(nB * sizeof(R) * 2 * (size_t)(T + 1));
     char *ref = take(nB * sizeof(R) * (size_t)ref_rows(T));
     if (w) {
         w->counts = (int *)counts;
         w->list[0] = (int *)l0; w->list[1] = (int *)l1;
         w->it = (int *)it; w->flags = (int *)flags;
-        w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0; w->J = (R *)J;
-        w->traj = (R *)traj; w->gains = (R *)gains; w->g = (R *)g; w->ref = (R *)ref;
+        w->dec = (int *)dec; w->keep = (unsigned *)keep;
+        w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0;
+        w->traj[0] = (R *)traj0; w->traj[1] = (R *)traj1; w->gains = (R *)gains; w->ref = (R *)ref;
     }
     return off;
 }
@@ -128,7 +129,7 @@ bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
     return true;
 }
 
-// One batched OCP: init, max_iter x (linearise, Riccati, line search, select), write-out.  Everything is
+// One batched OCP: init, max_iter x (Riccati, line search + selection, commit).  Everything is
 // stream-ordered; the host never waits, so all max_iter iterations are enqueued and the ones that find the
 // active list empty return at once.
 // candidates rolled out per thread of the line-search kernel (DTMPC_FWD_NC overrides, for tuning)
@@ -158,17 +159,17 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     const unsigned gFwd = (unsigned)((B + 31) / 32);
     for (int it = 0; it < P.ocp.max_iter; ++it) {
         ric_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
-        if (P.n_eval > 0) {
+        {
             const int nc = fwd_candidates_per_thread(P.n_eval);
-            const dim3 blk(32, (P.n_eval + nc - 1) / nc);
+            const int ny = (P.n_eval + nc - 1) / nc;
+            const dim3 blk(32, ny > 0 ? ny : 1);
             if (nc == 1) fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
             else if (nc == 2) fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
             else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);
         }
-        sel_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+        commit_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);  // the last iteration retires every instance still running
         P.parity ^= 1;
     }
-    out_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "iLQR kernel launch");
     return DTMPC_OK;
@@ -184,6 +185,11 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
     if (!io_ok(io0, true) || !io0->status) return fail(DTMPC_E_BADARG, "missing buffer in solve io");
     if (o1 && !io_ok(io1, false)) return fail(DTMPC_E_BADARG, "missing buffer in auxiliary solve io");
     if (!ws) return fail(DTMPC_E_BADARG, "null workspace");
+    for (const dtmpc_solve_io *s : {io0, io1}) {  // results are written with 16-byte vector stores
+        if (!s) continue;
+        for (const void *q : {(const void *)s->X, (const void *)s->V, (const void *)s->K, (const void *)s->kff})
+            if (((uintptr_t)q & 15u) != 0) return fail(DTMPC_E_BADARG, "result buffers must be 16-byte aligned");
+    }
     const int n_alpha = o1 && o1->n_alpha > o0->n_alpha ? o1->n_alpha : o0->n_alpha;
     if (ws_bytes < dtmpc_solve_workspace_bytes(o0->horizon, B, n_alpha, (int)sizeof(R)))
         return fail(DTMPC_E_WORKSPACE, "solve workspace too small");
@@ -203,7 +209,7 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
     int rc = launch_ocp(P, st);
     if (rc != DTMPC_OK || !o1) return rc;
 
-    // auxiliary OCP tracking the nominal solution that out_kernel left in ws.ref (core/tube_mpc.py:864-865)
+    // auxiliary OCP tracking the nominal solution that the commit sweep left in ws.ref (core/tube_mpc.py:864-865)
     convert_ocp(*o1, P.ocp);
     convert_io(*io1, P.io);
     P.io.status = io0->status;

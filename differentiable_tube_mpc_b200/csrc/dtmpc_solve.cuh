@@ -1,26 +1,33 @@
 // dtmpc_solve.cuh -- batched iLQR (reference core/ddp.py:102-307) as phase-synchronous kernels.
 //
-// The sweep is serial in T and the blocks are tiny (nx = 4, nu = 2): all parallelism is across the batch, and the
-// kernel is FP64-pipe bound, not HBM bound.  Every iLQR iteration of the whole batch is four launches over the list
-// of still-active instances:
+// The sweep is serial in T and the blocks are tiny (nx = 4, nu = 2): all parallelism is across the batch.  Every iLQR
+// iteration of the whole batch is three launches over the SLOTS that still hold a running instance:
 //
-//   ric_kernel   thread per instance               linearisation (from the stored barrier gradients g_k) + backward
+//   ric_kernel     thread per slot                 linearisation (from the stored barrier gradients g_k) + backward
 //                                                  Riccati sweep, register-resident V_x / V_xx, gains K, k
-//   fwd_kernel   thread per (instance, candidate)  forward line search: every alpha != 0 rolls out in its own lane,
-//                                                  one warp per candidate, 32 instances per CTA, so the gains and the
-//                                                  current trajectory are fetched once per CTA (L1) for all candidates;
-//                                                  only the candidate COST leaves the kernel
-//   sel_kernel   thread per instance               argmin (strict <, first wins), tolerance break, trace, compaction
-//                                                  of the active list, and the commit: the winner is rolled out once
-//                                                  more, in place (bit-identical to its candidate, dtmpc_math.cuh)
+//   fwd_kernel     thread per (slot, candidate)    forward line search: every alpha != 0 rolls out in its own lane, one
+//                                                  warp per candidate, 32 slots per CTA, so the gains and the current
+//                                                  trajectory are fetched once per CTA (L1) for all candidates; the
+//                                                  candidate costs meet in shared memory and warp 0 takes the decision
+//                                                  (argmin with strict <, tolerance break, trace): nothing but one int
+//                                                  per slot and one ballot per CTA leaves the kernel
+//   commit_kernel  thread per slot                 rolls the winner out once more (bit-identical to its candidate,
+//                                                  dtmpc_math.cuh) and writes it either into the slot the instance
+//                                                  holds in the NEXT iteration or, if the instance stops here, straight
+//                                                  into the caller's instance-major result tensors
 //
 // Candidate trajectories are never stored: storing all of them made the line search HBM-bound (2.6 GB per iteration
 // at B = 65,536, profiles/r01b), recomputing the winner costs 1/n_alpha more arithmetic and keeps one trajectory per
-// instance.  The alpha = 0 candidate is the current trajectory bit for bit and costs nothing.  Instances that have
-// converged leave the active list, so warps stay full while iteration counts differ (reference: 2..20 per instance).
+// instance.  The alpha = 0 candidate is the current trajectory bit for bit and costs nothing.
 //
-// Scratch is instance-minor structure-of-arrays (row r of instance i at base[r*B + i]): every access of a warp is a
-// contiguous segment.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
+// Slots, not instances, index the big scratch arrays (trajectory, barrier gradients, gains): row r of slot s lives at
+// base[r*B + s].  The commit sweep rewrites the whole trajectory every iteration anyway, so it writes it to the
+// instance's next slot (double-buffered), and the next slot is the instance's rank among the survivors: the running
+// instances always occupy slots 0 .. n_act-1 in ascending instance order.  Every access of a warp is then one full
+// contiguous segment however few instances are left, where an index list over instance-indexed arrays cost up to
+// 2.7x the traffic once a third of the batch had converged (profiles/r01c_iterations.txt).  Small per-instance
+// scalars and the tracked reference stay instance-indexed; the order-preserving compaction keeps those gathers
+// monotone.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
 #pragma once
 #include "dtmpc_math.cuh"
 
@@ -35,18 +42,19 @@ template <typename R> struct SolveArgs {
 };
 
 template <typename R> struct SolveWs {
-    int *counts;     // [2] sizes of the two active lists
-    int *list[2];    // active instance indices (double buffered)
-    int *it;         // [B] completed iterations
-    int *flags;      // [B] bit 0: non-finite in the backward pass
-    R *Jcur, *prev, *B0;  // [B] cost of the current trajectory, previous accepted cost, B(h(x0) - tight)
-    R *J;            // [n_alpha][B] candidate costs
-    R *traj;         // [4(T+1)+2T][B] current trajectory X, V
-    R *gains;        // [10T][B]  K (8 rows per k) then k (2 rows per k)
-    R *g;            // [2(T+1)][B] g_k = B'(h(x_k)) grad h(x_k): what the barrier row of the jacobian needs. Written by
-                     // whoever rolls the trajectory out (init, commit); a separate linearisation kernel and its 8 stored
-                     // jacobian entries per step made the backward pass HBM-bound (profiles/r01b)
-    R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)
+    int *counts;     // [2] number of occupied slots, per parity
+    int *list[2];    // [B] instance held by each slot (ascending), per parity
+    int *dec;        // [B] decision for the slot: bits 0-7 accepted candidate, bit 8 keeps running, bit 9 non-finite
+    unsigned *keep;  // [ceil(B/32)] ballot of 'keeps running' over each group of 32 slots
+    int *it;         // [B] completed iterations                         (per instance)
+    int *flags;      // [B] bit 0: non-finite in the backward pass       (per instance)
+    R *Jcur, *prev, *B0;  // [B] cost of the current trajectory, previous accepted cost, B(h(x0) - tight) (per instance)
+    R *traj[2];      // [4(T+1)+2T+2(T+1)][B] per slot and parity: X, V and g_k = B'(h(x_k)) grad h(x_k), which is what
+                     // the barrier row of the jacobian needs.  g is written by whoever rolls the trajectory out (init,
+                     // commit); a separate linearisation kernel and its 8 stored jacobian entries per step made the
+                     // backward pass HBM-bound (profiles/r01b)
+    R *gains;        // [10T][B] per slot: K (8 rows per k) then k (2 rows per k)
+    R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)  (per instance)
 };
 
 template <typename R> struct SolveParams {
@@ -59,14 +67,16 @@ template <typename R> struct SolveParams {
     int eval_idx[DTMPC_MAX_ALPHAS];  // their positions in the alpha list
     int use_ref;                     // 1: track ws.ref, 0: track io.target
     int ref_from_io;                 // 1: init copies io.Xref / io.Uref into ws.ref
-    int write_ref;                   // 1: out_kernel also writes ws.ref (nominal solution -> auxiliary reference)
+    int write_ref;                   // 1: a stopping instance also writes ws.ref (nominal solution -> auxiliary reference)
     int status_shift;                // 0 (single / nominal) or 4 (auxiliary)
-    int parity;                      // active list read by this launch
+    int parity;                      // slot assignment / trajectory buffer read by this launch
 };
 
 constexpr int LS_BLOCK = 128;
 
-__host__ __device__ inline long long traj_rows(int T) { return 4LL * (T + 1) + 2LL * T; }
+__host__ __device__ inline long long traj_rows(int T) { return 4LL * (T + 1) + 2LL * T + 2LL * (T + 1); }
+__host__ __device__ inline long long traj_v_row(int T) { return 4LL * (T + 1); }
+__host__ __device__ inline long long traj_g_row(int T) { return 4LL * (T + 1) + 2LL * T; }
 __host__ __device__ inline long long ref_rows(int T) { return 3LL * (T + 1) + 2LL * T; }
 
 template <typename R> struct RefPt { R x0, x1, x2, u0, u1; };
@@ -129,10 +139,10 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     State<R> x{x0p[0], x0p[1], x0p[2], x0p[3], R(0)};
     x.Bc = barrier_of_state(E, th, x.px, x.py);
     P.ws.B0[i] = x.Bc;
-    R *X = P.ws.traj + i;                       // buffer 0
-    R *V = X + 4LL * (T + 1) * S;
+    R *X = P.ws.traj[0] + i;                    // slot i of parity 0
+    R *V = X + traj_v_row(T) * S;
     X[0 * S] = x.px; X[1 * S] = x.py; X[2 * S] = x.th; X[3 * S] = x.b;
-    R *G = P.ws.g + i;
+    R *G = X + traj_g_row(T) * S;
     {
         R g0x, g0y, h0;
         barrier_grad(E, th, x.px, x.py, g0x, g0y, h0);
@@ -185,7 +195,6 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
-    if (j == 0) P.ws.counts[P.parity ^ 1] = 0;  // the list sel_kernel will fill (first kernel of the iteration)
     if (j >= n_act) return;
     const long long i = P.ws.list[P.parity][j];
     const long long S = P.B;
@@ -198,10 +207,10 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
-    const R *X = P.ws.traj + i;
-    const R *V = X + 4LL * (T + 1) * S;
-    const R *G = P.ws.g + i;
-    R *GK = P.ws.gains + i;
+    const R *X = P.ws.traj[P.parity] + j;
+    const R *V = X + traj_v_row(T) * S;
+    const R *G = X + traj_g_row(T) * S;
+    R *GK = P.ws.gains + j;
     R *Gk = GK + 8LL * T * S;
     const R reg = P.ocp.reg;
 
@@ -360,20 +369,27 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward line search (core/ddp.py:256-290).  blockDim = (32, ceil(n_eval / NC)): a CTA covers 32 instances; thread
-// (lane, g) rolls out candidates g*NC .. g*NC+NC-1 of its instance in lockstep.  NC independent dependency chains per
-// thread give the instruction-level parallelism a single fp64 chain lacks (DFMA latency 8.75 cycles, tools/micro), and
-// the gains / trajectory rows of a step are loaded once per thread for its NC candidates.  Only costs leave the kernel.
+// forward line search (core/ddp.py:256-290) and selection (core/ddp.py:293-305).  blockDim = (32, ceil(n_eval / NC)):
+// a CTA covers 32 slots; thread (lane, g) rolls out candidates g*NC .. g*NC+NC-1 of its slot in lockstep.  NC
+// independent dependency chains per thread give the instruction-level parallelism a single fp64 chain lacks (DFMA
+// latency 8.75 cycles, tools/micro), and the gains / trajectory rows of a step are loaded once per thread for its NC
+// candidates.  The costs meet in shared memory; warp 0 picks the winner (strict '<' in list order), applies the
+// tolerance break to the accepted costs and records the decision.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef DTMPC_FWD_MAXNREG
-#define DTMPC_FWD_MAXNREG 168
+#define DTMPC_FWD_MAXNREG 96
 #endif
+constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
+
 template <typename R, int NC>
 __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
+    __shared__ R sJ[DTMPC_MAX_ALPHAS * 32];
     const int n_act = P.ws.counts[P.parity];
-    const int j = blockIdx.x * 32 + threadIdx.x;
-    if (j >= n_act) return;
+    if ((int)blockIdx.x * 32 >= n_act) return;  // whole CTA
+    const int lane = threadIdx.x;
+    const bool live = (int)blockIdx.x * 32 + lane < n_act;
+    const int j = live ? blockIdx.x * 32 + lane : n_act - 1;  // idle lanes shadow the last slot (they reach the barrier)
     const long long i = P.ws.list[P.parity][j];
     const long long S = P.B;
     const EnvT<R> &E = P.env;
@@ -385,7 +401,7 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
     for (int q = 0; q < NC; ++q) {
         const int c = threadIdx.y * NC + q;
         valid[q] = c < P.n_eval;
-        a_idx[q] = P.eval_idx[valid[q] ? c : P.n_eval - 1];  // a padded slot repeats the last candidate
+        a_idx[q] = P.eval_idx[valid[q] ? c : (P.n_eval > 0 ? P.n_eval - 1 : 0)];  // a padded lane repeats a candidate
         al[q] = P.ocp.alphas[a_idx[q]];
     }
     Theta<R> th;
@@ -395,9 +411,9 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
-    const R *X = P.ws.traj + i;
-    const R *V = X + 4LL * (T + 1) * S;
-    const R *GK = P.ws.gains + i;
+    const R *X = P.ws.traj[P.parity] + j;
+    const R *V = X + traj_v_row(T) * S;
+    const R *GK = P.ws.gains + j;
     const R *Gk = GK + 8LL * T * S;
 
     State<R> x[NC];
@@ -438,34 +454,139 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         J[q] += terminal_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, r.x0, r.x1, r.x2);
-        if (valid[q]) P.ws.J[(long long)a_idx[q] * S + i] = J[q];
+        if (valid[q]) sJ[a_idx[q] * 32 + lane] = J[q];
     }
+    __syncthreads();
+    if (threadIdx.y != 0) return;
+
+    // selection: strict '<' in list order, tolerance break on the accepted costs (core/ddp.py:293-305)
+    bool keep = false;
+    if (live) {
+        const OcpT<R> &o = P.ocp;
+        const R Jc = P.ws.Jcur[i];
+        bool bad = (P.ws.flags[i] & 1) != 0;
+        int best_c = -1;
+        R best = R(0), second = m::inf_();
+        for (int c = 0; c < o.n_alpha; ++c) {
+            const R v = (o.alphas[c] == R(0)) ? Jc : sJ[c * 32 + lane];
+            bad |= !finite_(v);
+            if (best_c < 0 || v < best) {
+                if (best_c >= 0) second = m::min_(second, best);
+                best = v;
+                best_c = c;
+            } else {
+                second = m::min_(second, v);
+            }
+        }
+        int it = P.ws.it[i];
+        bool done = true;
+        if (!bad) {
+            if (o.alphas[best_c] != R(0)) P.ws.Jcur[i] = best;
+            if (P.io.alpha_idx) P.io.alpha_idx[i * o.max_iter + it] = best_c;
+            if (P.io.costs) P.io.costs[i * o.max_iter + it] = best;
+            if (P.io.margins) P.io.margins[i * o.max_iter + it] = second - best;
+            const bool conv = it > 0 && (m::abs_(P.ws.prev[i] - best) < o.tol);
+            P.ws.prev[i] = best;
+            ++it;
+            P.ws.it[i] = it;
+            done = conv || it >= o.max_iter;
+        } else {
+            P.io.status[i] |= DTMPC_ST_NONFINITE << P.status_shift;
+        }
+        keep = !done;
+        P.ws.dec[j] = best_c | (keep ? DEC_KEEP : 0) | (bad ? DEC_BAD : 0);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) P.ws.keep[blockIdx.x] = mask;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// commit sweep: read-ahead of one step under a 96-register cap measured best (25.65 vs 26.0 ms, same box)
+// commit sweep.  The accepted candidate is rolled out once more (for alpha = 0, or after a non-finite value, that is
+// the current trajectory itself).  An instance that keeps running gets the slot equal to its rank among the running
+// instances (prefix sum over the ballots fwd_kernel left), in the other trajectory buffer; an instance that stops
+// writes the caller's X, V (and K, k of its last backward pass, core/ddp.py:307) and, for the nominal OCP of a tube
+// solve, the reference the auxiliary OCP tracks.
+// Read-ahead of one step under a 96-register cap measured best (25.65 vs 26.0 ms per tube solve, same box).
+// ---------------------------------------------------------------------------------------------------------------
 #ifndef DTMPC_SEL_PREFETCH
-#define DTMPC_SEL_PREFETCH 1
+#define DTMPC_SEL_PREFETCH 0
 #endif
 #ifndef DTMPC_SEL_MAXNREG
-#define DTMPC_SEL_MAXNREG 96
+#define DTMPC_SEL_MAXNREG 128
 #endif
-// Rolls the accepted candidate out once more and overwrites the instance's trajectory in place (X_k of the old
-// trajectory is read before x_{k+1} of the new one lands in the next row).
-template <typename R> __device__ __forceinline__ void commit_candidate(const SolveParams<R> &P, long long i, R al) {
+__device__ __forceinline__ void st4(double *p, double a, double b, double c, double d) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
+}
+__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+__device__ __forceinline__ void st2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+
+template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
+    constexpr int NW = LS_BLOCK / 32;
+    __shared__ int s_part[NW];
+    const int n_act = P.ws.counts[P.parity];
+    if ((int)blockIdx.x * LS_BLOCK >= n_act) {  // whole CTA
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.ws.counts[P.parity ^ 1] = 0;
+        return;
+    }
+    const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rank of this CTA's first slot among the running instances
+    const int w0 = blockIdx.x * NW;
+    int acc = 0;
+    for (int w = threadIdx.x; w < w0; w += LS_BLOCK) acc += __popc(P.ws.keep[w]);
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (j >= n_act) return;
+    int base = 0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) base += s_part[q];
+    for (int q = 0; q < warp; ++q) base += __popc(P.ws.keep[w0 + q]);
+    const unsigned mine = P.ws.keep[w0 + warp];
+    if (j == n_act - 1) P.ws.counts[P.parity ^ 1] = base + __popc(mine);  // ballots are clear beyond the last slot
+
+    const int d = P.ws.dec[j];
+    const bool keep = (d & DEC_KEEP) != 0;
+    const long long i = P.ws.list[P.parity][j];
+    const long long jn = base + __popc(mine & ((1u << lane) - 1u));
+    if (keep) P.ws.list[P.parity ^ 1][jn] = (int)i;
+    const R al = (d & DEC_BAD) ? R(0) : P.ocp.alphas[d & 0xff];
+
     const long long S = P.B;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
-    R *X = P.ws.traj + i;
-    R *V = X + 4LL * (T + 1) * S;
-    R *G = P.ws.g + i;
-    const R *GK = P.ws.gains + i;
+    const R *X = P.ws.traj[P.parity] + j;
+    const R *V = X + traj_v_row(T) * S;
+    const R *GK = P.ws.gains + j;
     const R *Gk = GK + 8LL * T * S;
+    // destinations: next slot (running) or the result tensors (stopping)
+    R *Xn = P.ws.traj[P.parity ^ 1] + jn;
+    R *Vn = Xn + traj_v_row(T) * S;
+    R *Gn = Xn + traj_g_row(T) * S;
+    R *Xo = P.io.X + i * (4LL * (T + 1));
+    R *Vo = P.io.V + i * (2LL * T);
+    R *Ko = P.io.K ? P.io.K + i * (8LL * T) : nullptr;
+    R *ko = P.io.kff ? P.io.kff + i * (2LL * T) : nullptr;
+    R *Ro = P.write_ref ? P.ws.ref + i : nullptr;
+
     State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
     R X0 = x.px, X1 = x.py, X2 = x.th, X3 = x.b;
+    if (keep) {
+        const R *G = X + traj_g_row(T) * S;
+        Xn[0 * S] = X0; Xn[1 * S] = X1; Xn[2 * S] = X2; Xn[3 * S] = X3;
+        Gn[0 * S] = G[0 * S]; Gn[1 * S] = G[1 * S];
+    } else {
+        st4(Xo, X0, X1, X2, X3);
+        if (Ro) { Ro[0 * S] = X0; Ro[1 * S] = X1; Ro[2 * S] = X2; }
+        if (P.io.iters) P.io.iters[i] = P.ws.it[i];
+    }
     // inputs of step k+1 are fetched while step k computes (this sweep is the latency floor of an iteration)
     struct In {
         R v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1, N0, N1, N2, N3;
@@ -486,130 +607,47 @@ template <typename R> __device__ __forceinline__ void commit_candidate(const Sol
     for (int k = 0; k < T; ++k) {
         In nx;
 #if DTMPC_SEL_PREFETCH
-        load_step(k + 1 < T ? k + 1 : k, nx);  // rows k+2 are not written before step k+1: safe to read ahead
+        load_step(k + 1 < T ? k + 1 : k, nx);
 #else
         load_step(k, in);
         nx = in;
-#endif
-#if DTMPC_L2_PREFETCH > 0
-        if (k + 1 + DTMPC_L2_PREFETCH < T) {
-            const int kp = k + 1 + DTMPC_L2_PREFETCH;
-            for (int c = 0; c < 4; ++c) prefetch_l2(X + (4LL * (kp + 1) + c) * S);
-            for (int c = 0; c < 2; ++c) prefetch_l2(V + (2LL * kp + c) * S);
-            for (int c = 0; c < 8; ++c) prefetch_l2(GK + (8LL * kp + c) * S);
-            for (int c = 0; c < 2; ++c) prefetch_l2(Gk + (2LL * kp + c) * S);
-        }
 #endif
         const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
         const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
         const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
         R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
         clamp_u(E, u0, u1);
-        V[(2LL * k) * S] = u0;
-        V[(2LL * k + 1) * S] = u1;
+        if (d & DEC_BAD) { u0 = in.v0; u1 = in.v1; }  // non-finite gains must not leak into the trajectory that is kept
         R gx, gy;
         step_g(E, th, x, u0, u1, gx, gy);
-        X[(4LL * (k + 1) + 0) * S] = x.px;
-        X[(4LL * (k + 1) + 1) * S] = x.py;
-        X[(4LL * (k + 1) + 2) * S] = x.th;
-        X[(4LL * (k + 1) + 3) * S] = x.b;
-        G[(2LL * (k + 1) + 0) * S] = gx;
-        G[(2LL * (k + 1) + 1) * S] = gy;
+        if (keep) {
+            Vn[(2LL * k) * S] = u0;
+            Vn[(2LL * k + 1) * S] = u1;
+            Xn[(4LL * (k + 1) + 0) * S] = x.px;
+            Xn[(4LL * (k + 1) + 1) * S] = x.py;
+            Xn[(4LL * (k + 1) + 2) * S] = x.th;
+            Xn[(4LL * (k + 1) + 3) * S] = x.b;
+            Gn[(2LL * (k + 1) + 0) * S] = gx;
+            Gn[(2LL * (k + 1) + 1) * S] = gy;
+        } else {
+            st2(Vo + 2 * k, u0, u1);
+            st4(Xo + 4 * (k + 1), x.px, x.py, x.th, x.b);
+            if (Ko) {
+                st4(Ko + 8 * k, in.K00, in.K01, in.K02, in.K03);
+                st4(Ko + 8 * k + 4, in.K10, in.K11, in.K12, in.K13);
+            }
+            if (ko) st2(ko + 2 * k, in.k0, in.k1);
+            if (Ro) {
+                Ro[(3LL * (k + 1) + 0) * S] = x.px;
+                Ro[(3LL * (k + 1) + 1) * S] = x.py;
+                Ro[(3LL * (k + 1) + 2) * S] = x.th;
+                Ro[(3LL * (T + 1) + 2LL * k + 0) * S] = u0;
+                Ro[(3LL * (T + 1) + 2LL * k + 1) * S] = u1;
+            }
+        }
         X0 = in.N0; X1 = in.N1; X2 = in.N2; X3 = in.N3;
         in = nx;
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// selection (core/ddp.py:293-305): strict '<' in list order, tolerance break on the accepted costs, compaction
-// ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) sel_kernel(const __grid_constant__ SolveParams<R> P) {
-    using m = M<R>;
-    const int n_act = P.ws.counts[P.parity];
-    const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
-    bool keep = false;
-    long long i = -1;
-    if (j < n_act) {
-        i = P.ws.list[P.parity][j];
-        const long long S = P.B;
-        const OcpT<R> &o = P.ocp;
-        const R Jc = P.ws.Jcur[i];
-        bool bad = (P.ws.flags[i] & 1) != 0;
-        int best_c = -1;
-        R best = R(0), second = m::inf_();
-        for (int c = 0; c < o.n_alpha; ++c) {
-            const R v = (o.alphas[c] == R(0)) ? Jc : P.ws.J[(long long)c * S + i];
-            bad |= !finite_(v);
-            if (best_c < 0 || v < best) {
-                if (best_c >= 0) second = m::min_(second, best);
-                best = v;
-                best_c = c;
-            } else {
-                second = m::min_(second, v);
-            }
-        }
-        int it = P.ws.it[i];
-        bool done = true;
-        if (!bad) {
-            if (o.alphas[best_c] != R(0)) {
-                commit_candidate(P, i, o.alphas[best_c]);
-                P.ws.Jcur[i] = best;
-            }
-            if (P.io.alpha_idx) P.io.alpha_idx[i * o.max_iter + it] = best_c;
-            if (P.io.costs) P.io.costs[i * o.max_iter + it] = best;
-            if (P.io.margins) P.io.margins[i * o.max_iter + it] = second - best;
-            const bool conv = it > 0 && (m::abs_(P.ws.prev[i] - best) < o.tol);
-            P.ws.prev[i] = best;
-            ++it;
-            P.ws.it[i] = it;
-            done = conv || it >= o.max_iter;
-        } else {
-            P.io.status[i] |= DTMPC_ST_NONFINITE << P.status_shift;
-        }
-        keep = !done;
-    }
-    // order-preserving-within-warp compaction into the other list
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (mask) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == (__ffs(mask) - 1)) base = atomicAdd(&P.ws.counts[P.parity ^ 1], __popc(mask));
-        base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-        if (keep) P.ws.list[P.parity ^ 1][base + __popc(mask & ((1u << lane) - 1u))] = (int)i;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// results: instance-major copies of the accepted trajectory (and gains); nominal solution -> auxiliary reference
-// ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __launch_bounds__(LS_BLOCK) out_kernel(const __grid_constant__ SolveParams<R> P) {
-    const long long i = (long long)blockIdx.x * LS_BLOCK + threadIdx.x;
-    if (i >= P.B) return;
-    const long long S = P.B;
-    const int T = P.ocp.T;
-    const R *X = P.ws.traj + i;
-    const R *V = X + 4LL * (T + 1) * S;
-    R *Xo = P.io.X + i * (4LL * (T + 1));
-    R *Vo = P.io.V + i * (2LL * T);
-    for (int r = 0; r < 4 * (T + 1); ++r) Xo[r] = X[(long long)r * S];
-    for (int r = 0; r < 2 * T; ++r) Vo[r] = V[(long long)r * S];
-    if (P.write_ref) {
-        for (int k = 0; k <= T; ++k) {
-            P.ws.ref[(3LL * k + 0) * S + i] = X[(4LL * k + 0) * S];
-            P.ws.ref[(3LL * k + 1) * S + i] = X[(4LL * k + 1) * S];
-            P.ws.ref[(3LL * k + 2) * S + i] = X[(4LL * k + 2) * S];
-        }
-        for (int r = 0; r < 2 * T; ++r) P.ws.ref[(3LL * (T + 1) + r) * S + i] = V[(long long)r * S];
-    }
-    if (P.io.K) {
-        R *Ko = P.io.K + i * (8LL * T);
-        for (int r = 0; r < 8 * T; ++r) Ko[r] = P.ws.gains[(long long)r * S + i];
-    }
-    if (P.io.kff) {
-        R *ko = P.io.kff + i * (2LL * T);
-        for (int r = 0; r < 2 * T; ++r) ko[r] = P.ws.gains[(8LL * T + r) * S + i];
-    }
-    if (P.io.iters) P.io.iters[i] = P.ws.it[i];
 }
 
 }  // namespace dtmpc

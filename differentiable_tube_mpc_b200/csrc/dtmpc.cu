@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "dtmpc_math.cuh"
 #include "dtmpc_sens.cuh"
@@ -106,10 +107,10 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
     char *l0 = take(nB * sizeof(int)), *l1 = take(nB * sizeof(int));
     char *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
     char *Jcur = take(nB * sizeof(R)), *prev = take(nB * sizeof(R)), *B0 = take(nB * sizeof(R));
-    (void)n_alpha;  // candidate costs never leave the line-search kernel
     char *dec = take(nB * sizeof(int)), *keep = take((nB / 32 + 1) * sizeof(unsigned));
     char *traj0 = take(nB * sizeof(R) * (size_t)traj_rows(T)), *traj1 = take(nB * sizeof(R) * (size_t)traj_rows(T));
     char *gains = take(nB * sizeof(R) * 10 * (size_t)T);
+    char *ckpt = take(nB * sizeof(R) * 5 * (size_t)(MAX_SEG - 1) * (size_t)n_alpha);
     char *ref = take(nB * sizeof(R) * (size_t)ref_rows(T));
     if (w) {
         w->counts = (int *)counts;
@@ -117,7 +118,7 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
         w->it = (int *)it; w->flags = (int *)flags;
         w->dec = (int *)dec; w->keep = (unsigned *)keep;
         w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0;
-        w->traj[0] = (R *)traj0; w->traj[1] = (R *)traj1; w->gains = (R *)gains; w->ref = (R *)ref;
+        w->traj[0] = (R *)traj0; w->traj[1] = (R *)traj1; w->gains = (R *)gains; w->ckpt = (R *)ckpt; w->ref = (R *)ref;
     }
     return off;
 }
@@ -154,6 +155,10 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     P.n_eval = 0;
     for (int c = 0; c < P.ocp.n_alpha; ++c)
         if (P.ocp.alphas[c] != R(0)) P.eval_idx[P.n_eval++] = c;
+    for (int c = 0, q = 0; c < P.ocp.n_alpha; ++c) P.eval_pos[c] = P.ocp.alphas[c] != R(0) ? q++ : -1;
+    P.n_seg = T < MAX_SEG ? T : MAX_SEG;
+    P.seg_len = (T + P.n_seg - 1) / P.n_seg;
+    P.n_seg = (T + P.seg_len - 1) / P.seg_len;
     P.parity = 0;
     init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
     const unsigned gFwd = (unsigned)((B + 31) / 32);
@@ -167,12 +172,81 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
             else if (nc == 2) fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
             else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);
         }
-        commit_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);  // the last iteration retires every instance still running
+        commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);  // the last iteration retires every instance still running
         P.parity ^= 1;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "iLQR kernel launch");
     return DTMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Chunked execution.  The backward and commit sweeps are serial chains of T steps with one thread per instance: at
+// B = 65,536 they are a single wave of 14 warps per SM whose duration is the latency of one chain however few
+// instances are left, while the line search is bound by the fp64 pipe.  Contiguous chunks of the batch are
+// independent problems, so they run on their own streams and the sweeps of one chunk overlap the line search of
+// another.  Results do not depend on the chunking (every instance is computed by the same instruction sequence).
+// ---------------------------------------------------------------------------
+#ifndef DTMPC_DEFAULT_CHUNKS
+#define DTMPC_DEFAULT_CHUNKS 1
+#endif
+constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_DEVICES = 64;
+struct ChunkStreams {
+    cudaStream_t s[MAX_CHUNKS];
+    cudaEvent_t fork, done[MAX_CHUNKS];
+    bool ready = false;
+};
+ChunkStreams *chunk_streams() {
+    static ChunkStreams pool[MAX_DEVICES];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    ChunkStreams &c = pool[dev];
+    if (!c.ready) {
+        if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            if (cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        c.ready = true;
+    }
+    return &c;
+}
+int solve_chunks(long long B) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("DTMPC_CHUNKS");
+        forced = e ? atoi(e) : 0;
+    }
+    int n = forced > 0 ? forced : DTMPC_DEFAULT_CHUNKS;
+    if (n > MAX_CHUNKS) n = MAX_CHUNKS;
+    while (n > 1 && B / n < 8192) --n;  // a chunk should still fill the machine for the line search
+    return n < 1 ? 1 : n;
+}
+long long chunk_size(long long B, int n) {
+    const long long per = (B + n - 1) / n;
+    return (per + LS_BLOCK - 1) / LS_BLOCK * LS_BLOCK;
+}
+size_t chunked_ws_bytes_slack() { return (size_t)MAX_CHUNKS * 24 * 256; }
+
+template <typename R> void offset_io(SolveArgs<R> &a, long long off, int T, int max_iter) {
+    a.x0 += off * 4;
+    a.V_init += off * 2LL * T;
+    a.theta += off * a.theta_stride;
+    if (a.target) a.target += off * a.target_stride;
+    if (a.Xref) a.Xref += off * 3LL * (T + 1);
+    if (a.Uref) a.Uref += off * 2LL * T;
+    a.X += off * 4LL * (T + 1);
+    a.V += off * 2LL * T;
+    if (a.K) a.K += off * 8LL * T;
+    if (a.kff) a.kff += off * 2LL * T;
+    if (a.iters) a.iters += off;
+    if (a.status) a.status += off;
+    if (a.alpha_idx) a.alpha_idx += off * max_iter;
+    if (a.costs) a.costs += off * max_iter;
+    if (a.margins) a.margins += off * max_iter;
 }
 
 template <typename R>
@@ -193,31 +267,60 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
     const int n_alpha = o1 && o1->n_alpha > o0->n_alpha ? o1->n_alpha : o0->n_alpha;
     if (ws_bytes < dtmpc_solve_workspace_bytes(o0->horizon, B, n_alpha, (int)sizeof(R)))
         return fail(DTMPC_E_WORKSPACE, "solve workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
+    const cudaStream_t user = (cudaStream_t)stream;
+    const int T = o0->horizon;
 
-    SolveParams<R> P;
-    memset(&P, 0, sizeof(P));
-    convert_env(*env, P.env);
-    convert_ocp(*o0, P.ocp);
-    convert_io(*io0, P.io);
-    carve_solve_ws<R>((char *)ws, o0->horizon, B, n_alpha, &P.ws);
-    P.B = B;
-    P.use_ref = io0->Xref != nullptr;
-    P.ref_from_io = P.use_ref;
-    P.write_ref = o1 != nullptr;
-    P.status_shift = 0;
-    int rc = launch_ocp(P, st);
-    if (rc != DTMPC_OK || !o1) return rc;
-
-    // auxiliary OCP tracking the nominal solution that the commit sweep left in ws.ref (core/tube_mpc.py:864-865)
-    convert_ocp(*o1, P.ocp);
-    convert_io(*io1, P.io);
-    P.io.status = io0->status;
-    P.use_ref = 1;
-    P.ref_from_io = 0;
-    P.write_ref = 0;
-    P.status_shift = 4;
-    return launch_ocp(P, st);
+    int n_chunks = solve_chunks(B);
+    ChunkStreams *cs = n_chunks > 1 ? chunk_streams() : nullptr;
+    if (!cs) n_chunks = 1;
+    const long long per = chunk_size(B, n_chunks);
+    if (n_chunks > 1) {
+        cudaError_t e = cudaEventRecord(cs->fork, user);
+        if (e != cudaSuccess) return cuda_fail(e, "chunk fork");
+    }
+    size_t ws_off = 0;
+    int rc = DTMPC_OK;
+    for (int c = 0; c < n_chunks && rc == DTMPC_OK; ++c) {
+        const long long off = c * per;
+        if (off >= B) break;
+        const long long Bc = B - off < per ? B - off : per;
+        const cudaStream_t st = c == 0 ? user : cs->s[c];
+        if (c > 0) {
+            cudaError_t e = cudaStreamWaitEvent(st, cs->fork, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "chunk fork");
+        }
+        SolveParams<R> P;
+        memset(&P, 0, sizeof(P));
+        convert_env(*env, P.env);
+        convert_ocp(*o0, P.ocp);
+        convert_io(*io0, P.io);
+        offset_io(P.io, off, T, o0->max_iter);
+        ws_off += carve_solve_ws<R>((char *)ws + ws_off, T, Bc, n_alpha, &P.ws);
+        P.B = Bc;
+        P.use_ref = io0->Xref != nullptr;
+        P.ref_from_io = P.use_ref;
+        P.write_ref = o1 != nullptr;
+        P.status_shift = 0;
+        rc = launch_ocp(P, st);
+        if (rc == DTMPC_OK && o1) {
+            // auxiliary OCP tracking the nominal solution that the commit sweep left in ws.ref (core/tube_mpc.py:864-865)
+            convert_ocp(*o1, P.ocp);
+            convert_io(*io1, P.io);
+            P.io.status = io0->status;
+            offset_io(P.io, off, T, o1->max_iter);
+            P.use_ref = 1;
+            P.ref_from_io = 0;
+            P.write_ref = 0;
+            P.status_shift = 4;
+            rc = launch_ocp(P, st);
+        }
+        if (c > 0) {  // join, also after a failed launch: the caller's stream must not run ahead of the chunk
+            cudaError_t e = cudaEventRecord(cs->done[c], st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, cs->done[c], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "chunk join");
+        }
+    }
+    return rc;
 }
 
 template <typename R> void convert_sens(const dtmpc_sens_io &s, SensArgs<R> &a) {
@@ -500,8 +603,8 @@ const char *dtmpc_last_error(void) { return g_err; }
 
 size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size) {
     if (T < 1 || B < 0 || n_alpha < 1 || n_alpha > DTMPC_MAX_ALPHAS) return 0;
-    if (elem_size == 8) return carve_solve_ws<double>(nullptr, T, B, n_alpha, nullptr);
-    if (elem_size == 4) return carve_solve_ws<float>(nullptr, T, B, n_alpha, nullptr);
+    if (elem_size == 8) return carve_solve_ws<double>(nullptr, T, B, n_alpha, nullptr) + chunked_ws_bytes_slack();
+    if (elem_size == 4) return carve_solve_ws<float>(nullptr, T, B, n_alpha, nullptr) + chunked_ws_bytes_slack();
     return 0;
 }
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size) {

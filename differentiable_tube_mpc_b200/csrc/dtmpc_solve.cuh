@@ -11,10 +11,12 @@
 //                                                  candidate costs meet in shared memory and warp 0 takes the decision
 //                                                  (argmin with strict <, tolerance break, trace): nothing but one int
 //                                                  per slot and one ballot per CTA leaves the kernel
-//   commit_kernel  thread per slot                 rolls the winner out once more (bit-identical to its candidate,
-//                                                  dtmpc_math.cuh) and writes it either into the slot the instance
-//                                                  holds in the NEXT iteration or, if the instance stops here, straight
-//                                                  into the caller's instance-major result tensors
+//   commit_kernel  thread per (slot, segment)      rolls the winner out once more (bit-identical to its candidate,
+//                                                  dtmpc_math.cuh), every horizon segment in its own thread from the
+//                                                  state the candidate checkpointed at the segment boundary, and
+//                                                  writes it either into the slot the instance holds in the NEXT
+//                                                  iteration or, if the instance stops here, straight into the
+//                                                  caller's instance-major result tensors
 //
 // Candidate trajectories are never stored: storing all of them made the line search HBM-bound (2.6 GB per iteration
 // at B = 65,536, profiles/r01b), recomputing the winner costs 1/n_alpha more arithmetic and keeps one trajectory per
@@ -54,6 +56,7 @@ template <typename R> struct SolveWs {
                      // commit); a separate linearisation kernel and its 8 stored jacobian entries per step made the
                      // backward pass HBM-bound (profiles/r01b)
     R *gains;        // [10T][B] per slot: K (8 rows per k) then k (2 rows per k)
+    R *ckpt;         // [n_eval][MAX_SEG-1][5][B] per slot: state of every candidate at the segment boundaries
     R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)  (per instance)
 };
 
@@ -70,7 +73,10 @@ template <typename R> struct SolveParams {
     int write_ref;                   // 1: a stopping instance also writes ws.ref (nominal solution -> auxiliary reference)
     int status_shift;                // 0 (single / nominal) or 4 (auxiliary)
     int parity;                      // slot assignment / trajectory buffer read by this launch
+    int eval_pos[DTMPC_MAX_ALPHAS];  // inverse of eval_idx (-1 for alpha = 0)
+    int n_seg, seg_len;              // the commit sweep cuts the horizon into n_seg segments of seg_len steps
 };
+constexpr int MAX_SEG = 5;
 
 constexpr int LS_BLOCK = 128;
 
@@ -89,6 +95,16 @@ template <typename R> struct RefPt { R x0, x1, x2, u0, u1; };
 template <typename R> __device__ __forceinline__ void prefetch_l2(const R *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+
+// Asynchronous global -> shared copy of one element (LDGSTS): no destination register, so a sweep can keep the inputs
+// of several future steps in flight without paying for them in occupancy.  Every thread reads back only what it
+// copied itself, so cp.async.wait_group is all the synchronisation there is.
+template <typename R> __device__ __forceinline__ void cp_async_elem(R *smem_dst, const R *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(sizeof(R)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename R>
 __device__ __forceinline__ void ref_at(const SolveParams<R> &P, long long i, int k, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
@@ -231,7 +247,6 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     const R lxx0 = R(2) * th.Q0, lxx1 = R(2) * th.Q1, lxx2 = R(2) * th.Q2, lxx3 = R(2) * th.qb;
     const R luu0 = R(2) * th.R0, luu1 = R(2) * th.R1;
     const R gam = th.gamma, dt = E.dt;
-    bool bad = false;
     // inputs of step k are fetched one step ahead of their use (see fwd_kernel)
     struct RicIn {
         R px, py, pt, pb, u0, u1;
@@ -359,13 +374,13 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         ENT_V(2, 0) ENT_V(2, 1) ENT_V(2, 2) ENT_V(2, 3)
         ENT_V(3, 0) ENT_V(3, 1) ENT_V(3, 2) ENT_V(3, 3)
 #undef ENT_V
-        // non-finite guard (the reference raises: core/ddp.py:225-254)
-        const R chk = (Vx0 + Vx1) + (Vx2 + Vx3) + (k0 + k1) + (K00 + K01) + (K02 + K03) + (K10 + K11) + (K12 + K13) +
-                      (V00 + V11) + (V22 + V33) + (V01 + V02) + (V03 + V12) + (V13 + V23) + (V10 + V20) + (V30 + V21) +
-                      (V31 + V32);
-        bad |= !finite_(chk);
     }
-    if (bad) P.ws.flags[i] |= 1;
+    // non-finite guard (the reference raises: core/ddp.py:225-254).  One test after the sweep sees everything: every
+    // entry of V_xx / V_x feeds the same entry one step earlier (A = I + ...), and every gain feeds V_xx or V_x of its
+    // own step, so a NaN or Inf produced anywhere is still there at k = 0.
+    const R chk = (Vx0 + Vx1) + (Vx2 + Vx3) + (V00 + V11) + (V22 + V33) + (V01 + V02) + (V03 + V12) + (V13 + V23) +
+                  (V10 + V20) + (V30 + V21) + (V31 + V32);
+    if (!finite_(chk)) P.ws.flags[i] |= 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -426,7 +441,20 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
             J[q] = R(0);
         }
     }
+    int k_ck = P.seg_len, seg = 0;  // next segment boundary
     for (int k = 0; k < T; ++k) {
+        if (k == k_ck) {  // the commit sweep restarts the winner from here (uniform branch)
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < NC; ++q) {
+                    if (!valid[q]) continue;
+                    R *c = P.ws.ckpt + ((long long)((threadIdx.y * NC + q) * (MAX_SEG - 1) + seg) * 5) * S + j;
+                    c[0 * S] = x[q].px; c[1 * S] = x[q].py; c[2 * S] = x[q].th; c[3 * S] = x[q].b; c[4 * S] = x[q].Bc;
+                }
+            }
+            k_ck += P.seg_len;
+            ++seg;
+        }
         const R X0 = X[(4LL * k + 0) * S], X1 = X[(4LL * k + 1) * S], X2 = X[(4LL * k + 2) * S], X3 = X[(4LL * k + 3) * S];
         const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
         const R *o = GK + (8LL * k) * S;
@@ -501,18 +529,17 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// commit sweep.  The accepted candidate is rolled out once more (for alpha = 0, or after a non-finite value, that is
-// the current trajectory itself).  An instance that keeps running gets the slot equal to its rank among the running
-// instances (prefix sum over the ballots fwd_kernel left), in the other trajectory buffer; an instance that stops
-// writes the caller's X, V (and K, k of its last backward pass, core/ddp.py:307) and, for the nominal OCP of a tube
-// solve, the reference the auxiliary OCP tracks.
-// Read-ahead of one step under a 96-register cap measured best (25.65 vs 26.0 ms per tube solve, same box).
+// commit sweep, blockDim = (32, n_seg).  The accepted candidate is rolled out once more, each horizon segment by its
+// own thread: one chain of T steps per instance is a single wave of 14 warps per SM at B = 65,536 and costs the
+// latency of that chain whatever the batch, n_seg chains of T/n_seg steps fill the machine.  A segment starts from
+// the state its candidate checkpointed in fwd_kernel, so it repeats the candidate's operations exactly.  When alpha = 0
+// wins, or a value was non-finite, the current trajectory is kept: those lanes copy it.  An instance that keeps
+// running gets the slot equal to its rank among the running instances (prefix sum over the ballots fwd_kernel left),
+// in the other trajectory buffer; an instance that stops writes the caller's X, V (and K, k of its last backward
+// pass, core/ddp.py:307) and, for the nominal OCP of a tube solve, the reference the auxiliary OCP tracks.
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef DTMPC_SEL_PREFETCH
-#define DTMPC_SEL_PREFETCH 0
-#endif
 #ifndef DTMPC_SEL_MAXNREG
-#define DTMPC_SEL_MAXNREG 128
+#define DTMPC_SEL_MAXNREG 96
 #endif
 __device__ __forceinline__ void st4(double *p, double a, double b, double c, double d) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
@@ -526,44 +553,43 @@ __device__ __forceinline__ void st2(float *p, float a, float b) { *reinterpret_c
 
 template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
-    constexpr int NW = LS_BLOCK / 32;
-    __shared__ int s_part[NW];
+    __shared__ int s_part[MAX_SEG];
     const int n_act = P.ws.counts[P.parity];
-    if ((int)blockIdx.x * LS_BLOCK >= n_act) {  // whole CTA
-        if (blockIdx.x == 0 && threadIdx.x == 0) P.ws.counts[P.parity ^ 1] = 0;
+    if ((int)blockIdx.x * 32 >= n_act) {  // whole CTA
+        if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) P.ws.counts[P.parity ^ 1] = 0;
         return;
     }
-    const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x, seg = threadIdx.y;
+    const int j = blockIdx.x * 32 + lane;
     // rank of this CTA's first slot among the running instances
-    const int w0 = blockIdx.x * NW;
     int acc = 0;
-    for (int w = threadIdx.x; w < w0; w += LS_BLOCK) acc += __popc(P.ws.keep[w]);
+    for (int w = seg * 32 + lane; w < (int)blockIdx.x; w += 32 * blockDim.y) acc += __popc(P.ws.keep[w]);
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) s_part[warp] = acc;
+    if (lane == 0) s_part[seg] = acc;
     __syncthreads();
     if (j >= n_act) return;
     int base = 0;
-#pragma unroll
-    for (int q = 0; q < NW; ++q) base += s_part[q];
-    for (int q = 0; q < warp; ++q) base += __popc(P.ws.keep[w0 + q]);
-    const unsigned mine = P.ws.keep[w0 + warp];
-    if (j == n_act - 1) P.ws.counts[P.parity ^ 1] = base + __popc(mine);  // ballots are clear beyond the last slot
+    for (int q = 0; q < (int)blockDim.y; ++q) base += s_part[q];
+    const unsigned mine = P.ws.keep[blockIdx.x];
+    if (j == n_act - 1 && seg == 0) P.ws.counts[P.parity ^ 1] = base + __popc(mine);  // ballots are clear beyond n_act
 
     const int d = P.ws.dec[j];
     const bool keep = (d & DEC_KEEP) != 0;
     const long long i = P.ws.list[P.parity][j];
     const long long jn = base + __popc(mine & ((1u << lane) - 1u));
-    if (keep) P.ws.list[P.parity ^ 1][jn] = (int)i;
+    if (keep && seg == 0) P.ws.list[P.parity ^ 1][jn] = (int)i;
     const R al = (d & DEC_BAD) ? R(0) : P.ocp.alphas[d & 0xff];
+    const bool copy = al == R(0);  // the current trajectory stays
 
     const long long S = P.B;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
+    const int k_lo = seg * P.seg_len, k_hi = min(T, k_lo + P.seg_len);
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
     const R *X = P.ws.traj[P.parity] + j;
     const R *V = X + traj_v_row(T) * S;
+    const R *G = X + traj_g_row(T) * S;
     const R *GK = P.ws.gains + j;
     const R *Gk = GK + 8LL * T * S;
     // destinations: next slot (running) or the result tensors (stopping)
@@ -576,50 +602,45 @@ template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kern
     R *ko = P.io.kff ? P.io.kff + i * (2LL * T) : nullptr;
     R *Ro = P.write_ref ? P.ws.ref + i : nullptr;
 
-    State<R> x{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
-    R X0 = x.px, X1 = x.py, X2 = x.th, X3 = x.b;
-    if (keep) {
-        const R *G = X + traj_g_row(T) * S;
-        Xn[0 * S] = X0; Xn[1 * S] = X1; Xn[2 * S] = X2; Xn[3 * S] = X3;
-        Gn[0 * S] = G[0 * S]; Gn[1 * S] = G[1 * S];
-    } else {
-        st4(Xo, X0, X1, X2, X3);
-        if (Ro) { Ro[0 * S] = X0; Ro[1 * S] = X1; Ro[2 * S] = X2; }
-        if (P.io.iters) P.io.iters[i] = P.ws.it[i];
+    // state at the head of the segment: x_0, or the winner's checkpoint; and the old trajectory's state there
+    R X0 = X[(4LL * k_lo + 0) * S], X1 = X[(4LL * k_lo + 1) * S], X2 = X[(4LL * k_lo + 2) * S], X3 = X[(4LL * k_lo + 3) * S];
+    State<R> x{X0, X1, X2, X3, R(0)};
+    if (seg == 0) {
+        x.Bc = P.ws.B0[i];
+        if (keep) {
+            Xn[0 * S] = X0; Xn[1 * S] = X1; Xn[2 * S] = X2; Xn[3 * S] = X3;
+            Gn[0 * S] = G[0 * S]; Gn[1 * S] = G[1 * S];
+        } else {
+            st4(Xo, X0, X1, X2, X3);
+            if (Ro) { Ro[0 * S] = X0; Ro[1 * S] = X1; Ro[2 * S] = X2; }
+            if (P.io.iters) P.io.iters[i] = P.ws.it[i];
+        }
+    } else if (!copy) {
+        const R *c = P.ws.ckpt + ((long long)(P.eval_pos[d & 0xff] * (MAX_SEG - 1) + (seg - 1)) * 5) * S + j;
+        x.px = c[0 * S]; x.py = c[1 * S]; x.th = c[2 * S]; x.b = c[3 * S]; x.Bc = c[4 * S];
     }
-    // inputs of step k+1 are fetched while step k computes (this sweep is the latency floor of an iteration)
-    struct In {
-        R v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1, N0, N1, N2, N3;
-    };
-    auto load_step = [&](int k, In &q) {
-        q.v0 = V[(2LL * k) * S]; q.v1 = V[(2LL * k + 1) * S];
+    for (int k = k_lo; k < k_hi; ++k) {
+        const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
         const R *o = GK + (8LL * k) * S;
-        q.K00 = o[0 * S]; q.K01 = o[1 * S]; q.K02 = o[2 * S]; q.K03 = o[3 * S];
-        q.K10 = o[4 * S]; q.K11 = o[5 * S]; q.K12 = o[6 * S]; q.K13 = o[7 * S];
-        q.k0 = Gk[(2LL * k) * S]; q.k1 = Gk[(2LL * k + 1) * S];
-        q.N0 = X[(4LL * (k + 1) + 0) * S]; q.N1 = X[(4LL * (k + 1) + 1) * S];
-        q.N2 = X[(4LL * (k + 1) + 2) * S]; q.N3 = X[(4LL * (k + 1) + 3) * S];
-    };
-    In in;
-#if DTMPC_SEL_PREFETCH
-    load_step(0, in);
-#endif
-    for (int k = 0; k < T; ++k) {
-        In nx;
-#if DTMPC_SEL_PREFETCH
-        load_step(k + 1 < T ? k + 1 : k, nx);
-#else
-        load_step(k, in);
-        nx = in;
-#endif
-        const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
-        const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
-        const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
-        R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
-        clamp_u(E, u0, u1);
-        if (d & DEC_BAD) { u0 = in.v0; u1 = in.v1; }  // non-finite gains must not leak into the trajectory that is kept
-        R gx, gy;
-        step_g(E, th, x, u0, u1, gx, gy);
+        const R K00 = o[0 * S], K01 = o[1 * S], K02 = o[2 * S], K03 = o[3 * S];
+        const R K10 = o[4 * S], K11 = o[5 * S], K12 = o[6 * S], K13 = o[7 * S];
+        const R k0 = Gk[(2LL * k) * S], k1 = Gk[(2LL * k + 1) * S];
+        const R N0 = X[(4LL * (k + 1) + 0) * S], N1 = X[(4LL * (k + 1) + 1) * S];
+        const R N2 = X[(4LL * (k + 1) + 2) * S], N3 = X[(4LL * (k + 1) + 3) * S];
+        R u0 = v0, u1 = v1, gx, gy;
+        if (!copy) {
+            const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
+            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
+            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
+            u0 = m::fma_(al, du0, v0);
+            u1 = m::fma_(al, du1, v1);
+            clamp_u(E, u0, u1);
+            step_g(E, th, x, u0, u1, gx, gy);
+        } else {
+            x.px = N0; x.py = N1; x.th = N2; x.b = N3;
+            gx = G[(2LL * (k + 1) + 0) * S];
+            gy = G[(2LL * (k + 1) + 1) * S];
+        }
         if (keep) {
             Vn[(2LL * k) * S] = u0;
             Vn[(2LL * k + 1) * S] = u1;
@@ -633,10 +654,10 @@ template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kern
             st2(Vo + 2 * k, u0, u1);
             st4(Xo + 4 * (k + 1), x.px, x.py, x.th, x.b);
             if (Ko) {
-                st4(Ko + 8 * k, in.K00, in.K01, in.K02, in.K03);
-                st4(Ko + 8 * k + 4, in.K10, in.K11, in.K12, in.K13);
+                st4(Ko + 8 * k, K00, K01, K02, K03);
+                st4(Ko + 8 * k + 4, K10, K11, K12, K13);
             }
-            if (ko) st2(ko + 2 * k, in.k0, in.k1);
+            if (ko) st2(ko + 2 * k, k0, k1);
             if (Ro) {
                 Ro[(3LL * (k + 1) + 0) * S] = x.px;
                 Ro[(3LL * (k + 1) + 1) * S] = x.py;
@@ -645,8 +666,7 @@ template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kern
                 Ro[(3LL * (T + 1) + 2LL * k + 1) * S] = u1;
             }
         }
-        X0 = in.N0; X1 = in.N1; X2 = in.N2; X3 = in.N3;
-        in = nx;
+        X0 = N0; X1 = N1; X2 = N2; X3 = N3;
     }
 }
 

@@ -102,16 +102,16 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
         off = align_up(off + bytes);
         return p;
     };
-    const size_t nB = (size_t)B;
+    const size_t nB = (size_t)B, nT = (size_t)((B + 31) / 32) * 32;  // tile-major arrays cover whole tiles
     char *counts = take(256);
     char *l0 = take(nB * sizeof(int)), *l1 = take(nB * sizeof(int));
     char *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
     char *Jcur = take(nB * sizeof(R)), *prev = take(nB * sizeof(R)), *B0 = take(nB * sizeof(R));
     char *dec = take(nB * sizeof(int)), *keep = take((nB / 32 + 1) * sizeof(unsigned));
-    char *traj0 = take(nB * sizeof(R) * (size_t)traj_rows(T)), *traj1 = take(nB * sizeof(R) * (size_t)traj_rows(T));
-    char *gains = take(nB * sizeof(R) * 10 * (size_t)T);
-    char *ckpt = take(nB * sizeof(R) * 5 * (size_t)(MAX_SEG - 1) * (size_t)n_alpha);
-    char *ref = take(nB * sizeof(R) * (size_t)ref_rows(T));
+    char *traj0 = take(nT * sizeof(R) * (size_t)traj_rows(T)), *traj1 = take(nT * sizeof(R) * (size_t)traj_rows(T));
+    char *gains = take(nT * sizeof(R) * (size_t)gain_rows(T));
+    char *ckpt = take(nT * sizeof(R) * CR * (size_t)(MAX_SEG - 1) * (size_t)n_alpha);
+    char *ref = take(nT * sizeof(R) * (size_t)ref_rows(T));
     if (w) {
         w->counts = (int *)counts;
         w->list[0] = (int *)l0; w->list[1] = (int *)l1;
@@ -159,6 +159,9 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     P.n_seg = T < MAX_SEG ? T : MAX_SEG;
     P.seg_len = (T + P.n_seg - 1) / P.n_seg;
     P.n_seg = (T + P.seg_len - 1) / P.seg_len;
+    // kernels with the obstacle count fixed at compile time exist for the reference scenario (5 circles, smooth-min)
+    static const bool allow_fixed = !getenv("DTMPC_NO_FIXED_NOBS");
+    const int fixed_nobs = (allow_fixed && P.env.agg == DTMPC_AGG_SMOOTHMIN) ? P.env.n_obs : -1;
     P.parity = 0;
     init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
     const unsigned gFwd = (unsigned)((B + 31) / 32);
@@ -168,11 +171,14 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
             const int nc = fwd_candidates_per_thread(P.n_eval);
             const int ny = (P.n_eval + nc - 1) / nc;
             const dim3 blk(32, ny > 0 ? ny : 1);
-            if (nc == 1) fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
+            if (nc == 1 && fixed_nobs == 5) fwd_kernel<R, 1, 5><<<gFwd, blk, 0, st>>>(P);
+            else if (nc == 1) fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
             else if (nc == 2) fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
             else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);
         }
-        commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);  // the last iteration retires every instance still running
+        // the last iteration retires every instance still running
+        if (fixed_nobs == 5) commit_kernel<R, 5><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
+        else commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
         P.parity ^= 1;
     }
     cudaError_t e = cudaGetLastError();
@@ -188,7 +194,7 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
 // another.  Results do not depend on the chunking (every instance is computed by the same instruction sequence).
 // ---------------------------------------------------------------------------
 #ifndef DTMPC_DEFAULT_CHUNKS
-#define DTMPC_DEFAULT_CHUNKS 1
+#define DTMPC_DEFAULT_CHUNKS 2
 #endif
 constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_DEVICES = 64;

@@ -10,6 +10,7 @@
 // function; evaluation order follows them except where a dense product with
 // structural zeros/ones is written out sparsely (adding exact zeros).
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -250,17 +251,52 @@ __device__ __forceinline__ void load_theta(Theta<R> &t, const R *__restrict__ p,
 //   single circle: h_0, 2(p - c_0)                   :16-38
 //   empty list: h = 1, grad = 0                      :57-61, 81-82
 // ---------------------------------------------------------------------------
-template <typename R, bool GRAD>
+// NOBS > 0 fixes the obstacle count at compile time for a smooth-min environment (the hot kernels are instantiated
+// for the counts in DTMPC_FIXED_NOBS_LIST): the obstacle loop unrolls, its first three insertions lose the compares
+// against -inf, and the aggregation-mode branches disappear.  The arithmetic per point is unchanged.
+template <typename R, int I> __device__ __forceinline__ void top3_insert(R z, R &z1, R &z2, R &z3, bool &p1, bool &p2) {
+    if (I == 0) {  // z1 = z2 = z3 = -inf before the first obstacle
+        p1 = true; p2 = true;
+        z1 = z;
+    } else if (I == 1) {
+        p1 = z > z1; p2 = true;
+        z2 = p1 ? z1 : z;
+        z1 = p1 ? z : z1;
+    } else if (I == 2) {
+        p1 = z > z1; p2 = z > z2;
+        z3 = p2 ? z2 : z;
+        z2 = p1 ? z1 : (p2 ? z : z2);
+        z1 = p1 ? z : z1;
+    } else {
+        p1 = z > z1; p2 = z > z2;
+        const bool p3 = z > z3;
+        z3 = p2 ? z2 : (p3 ? z : z3);
+        z2 = p1 ? z1 : (p2 ? z : z2);
+        z1 = p1 ? z : z1;
+    }
+}
+template <int I, int N> struct ObsLoop {  // compile-time obstacle index
+    template <typename F> __device__ __forceinline__ static void run(F &&f) {
+        f(std::integral_constant<int, I>{});
+        ObsLoop<I + 1, N>::run(f);
+    }
+};
+template <int N> struct ObsLoop<N, N> {
+    template <typename F> __device__ __forceinline__ static void run(F &&) {}
+};
+
+template <typename R, bool GRAD, int NOBS = -1>
 __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx, R &gy) {
     using m = M<R>;
-    const int n = e.n_obs;
+    constexpr bool FIX = NOBS > 0;
+    const int n = FIX ? NOBS : e.n_obs;
     gx = R(0);
     gy = R(0);
-    if (n == 0) {
+    if (!FIX && n == 0) {
         h = R(1);
         return;
     }
-    if (e.agg == DTMPC_AGG_SINGLE) {
+    if (!FIX && e.agg == DTMPC_AGG_SINGLE) {
         R dx = px - e.cx[0], dy = py - e.cy[0];
         h = m::fma_(dy, dy, dx * dx) - e.r2[0];
         if (GRAD) {
@@ -269,7 +305,7 @@ __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx
         }
         return;
     }
-    if (e.agg == DTMPC_AGG_MIN) {
+    if (!FIX && e.agg == DTMPC_AGG_MIN) {
         R best = m::inf_();
         R bx = R(0), by = R(0);
         for (int i = 0; i < n; ++i) {
@@ -296,25 +332,47 @@ __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx
     // whatever the neighbouring lanes do).
     R z1 = -m::inf_(), z2 = -m::inf_(), z3 = -m::inf_();
     R ax1 = R(0), ay1 = R(0), ax2 = R(0), ay2 = R(0);
-    for (int i = 0; i < n; ++i) {
-        const R dx = px - e.cx[i], dy = py - e.cy[i];
-        const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
-        const R z = e.nbeta * hi;
-        const bool p1 = z > z1, p2 = z > z2, p3 = z > z3;
-        z3 = p2 ? z2 : (p3 ? z : z3);
-        z2 = p1 ? z1 : (p2 ? z : z2);
-        z1 = p1 ? z : z1;
-        if (GRAD) {
-            ax2 = p1 ? ax1 : (p2 ? dx : ax2);
-            ay2 = p1 ? ay1 : (p2 ? dy : ay2);
-            ax1 = p1 ? dx : ax1;
-            ay1 = p1 ? dy : ay1;
+    if (FIX) {
+        ObsLoop<0, FIX ? NOBS : 0>::run([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const R dx = px - e.cx[i], dy = py - e.cy[i];
+            const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+            const R z = e.nbeta * hi;
+            bool p1, p2;
+            top3_insert<R, i>(z, z1, z2, z3, p1, p2);
+            if (GRAD) {
+                if (i == 0) {
+                    ax1 = dx; ay1 = dy;
+                } else {
+                    ax2 = p1 ? ax1 : (p2 ? dx : ax2);
+                    ay2 = p1 ? ay1 : (p2 ? dy : ay2);
+                    ax1 = p1 ? dx : ax1;
+                    ay1 = p1 ? dy : ay1;
+                }
+            }
+        });
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const R dx = px - e.cx[i], dy = py - e.cy[i];
+            const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
+            const R z = e.nbeta * hi;
+            const bool p1 = z > z1, p2 = z > z2, p3 = z > z3;
+            z3 = p2 ? z2 : (p3 ? z : z3);
+            z2 = p1 ? z1 : (p2 ? z : z2);
+            z1 = p1 ? z : z1;
+            if (GRAD) {
+                ax2 = p1 ? ax1 : (p2 ? dx : ax2);
+                ay2 = p1 ? ay1 : (p2 ? dy : ay2);
+                ax1 = p1 ? dx : ax1;
+                ay1 = p1 ? dy : ay1;
+            }
         }
     }
     const R reach = sizeof(R) == 8 ? R(-40) : R(-18);
     R s, sx = R(0), sy = R(0);
     if (z3 - z1 > reach) {
         s = R(0);
+#pragma unroll 1
         for (int i = 0; i < n; ++i) {
             const R dx = px - e.cx[i], dy = py - e.cy[i];
             const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
@@ -390,16 +448,17 @@ template <typename R> __device__ __forceinline__ R wrap_angle(R err) {
 // parallelism: a lone fp64 dependency chain issues once per ~9 cycles).  Per point the arithmetic is exactly that of
 // eval_h<R, false>; every rollout in the library goes through this function, so results are bit-identical wherever a
 // state is propagated (initial rollout, candidates, commit, plant step).
-template <typename R, int NC>
+template <typename R, int NC, int NOBS = -1>
 __device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC], const R (&py)[NC], R (&h)[NC]) {
     using m = M<R>;
-    const int n = e.n_obs;
-    if (n == 0) {
+    constexpr bool FIX = NOBS > 0;
+    const int n = FIX ? NOBS : e.n_obs;
+    if (!FIX && n == 0) {
 #pragma unroll
         for (int q = 0; q < NC; ++q) h[q] = R(1);
         return;
     }
-    if (e.agg == DTMPC_AGG_SINGLE) {
+    if (!FIX && e.agg == DTMPC_AGG_SINGLE) {
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
             const R dx = px[q] - e.cx[0], dy = py[q] - e.cy[0];
@@ -407,7 +466,7 @@ __device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC]
         }
         return;
     }
-    if (e.agg == DTMPC_AGG_MIN) {
+    if (!FIX && e.agg == DTMPC_AGG_MIN) {
         R best[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) best[q] = m::inf_();
@@ -427,17 +486,31 @@ __device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC]
     R z1[NC], z2[NC], z3[NC];
 #pragma unroll
     for (int q = 0; q < NC; ++q) z1[q] = z2[q] = z3[q] = -m::inf_();
-    for (int i = 0; i < n; ++i) {
-        const R cx = e.cx[i], cy = e.cy[i], r2 = e.r2[i];
+    if (FIX) {
+        ObsLoop<0, FIX ? NOBS : 0>::run([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const R cx = e.cx[i], cy = e.cy[i], r2 = e.r2[i];
 #pragma unroll
-        for (int q = 0; q < NC; ++q) {
-            const R dx = px[q] - cx, dy = py[q] - cy;
-            const R hi = m::fma_(dy, dy, dx * dx) - r2;
-            const R z = e.nbeta * hi;
-            const bool p1 = z > z1[q], p2 = z > z2[q], p3 = z > z3[q];
-            z3[q] = p2 ? z2[q] : (p3 ? z : z3[q]);
-            z2[q] = p1 ? z1[q] : (p2 ? z : z2[q]);
-            z1[q] = p1 ? z : z1[q];
+            for (int q = 0; q < NC; ++q) {
+                const R dx = px[q] - cx, dy = py[q] - cy;
+                const R hi = m::fma_(dy, dy, dx * dx) - r2;
+                bool p1, p2;
+                top3_insert<R, i>(e.nbeta * hi, z1[q], z2[q], z3[q], p1, p2);
+            }
+        });
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const R cx = e.cx[i], cy = e.cy[i], r2 = e.r2[i];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                const R dx = px[q] - cx, dy = py[q] - cy;
+                const R hi = m::fma_(dy, dy, dx * dx) - r2;
+                const R z = e.nbeta * hi;
+                const bool p1 = z > z1[q], p2 = z > z2[q], p3 = z > z3[q];
+                z3[q] = p2 ? z2[q] : (p3 ? z : z3[q]);
+                z2[q] = p1 ? z1[q] : (p2 ? z : z2[q]);
+                z1[q] = p1 ? z : z1[q];
+            }
         }
     }
     const R reach = sizeof(R) == 8 ? R(-40) : R(-18);
@@ -453,6 +526,7 @@ __device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC]
         for (int q = 0; q < NC; ++q) {
             if (z3[q] - z1[q] > reach) {
                 R acc = R(0);
+#pragma unroll 1
                 for (int i = 0; i < n; ++i) {
                     const R dx = px[q] - e.cx[i], dy = py[q] - e.cy[i];
                     const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
@@ -491,7 +565,7 @@ __device__ __forceinline__ R barrier_of_state(const EnvT<R> &e, const Theta<R> &
 }
 
 // One step of f_hat for NC states: dubins_step (core/systems/dubins.py:36-42) + dbas_step (core/barrier.py:93-108).
-template <typename R, int NC>
+template <typename R, int NC, int NOBS = -1>
 __device__ __forceinline__ void step_multi(const EnvT<R> &e, const Theta<R> &t, State<R> (&x)[NC], const R (&u0)[NC],
                                            const R (&u1)[NC]) {
     using m = M<R>;
@@ -505,7 +579,7 @@ __device__ __forceinline__ void step_multi(const EnvT<R> &e, const Theta<R> &t, 
         pyn[q] = m::fma_(dtv, s, x[q].py);
         thn[q] = m::fma_(e.dt, u1[q], x[q].th);
     }
-    eval_h_multi<R, NC>(e, pxn, pyn, h);
+    eval_h_multi<R, NC, NOBS>(e, pxn, pyn, h);
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         const R Bn = barrier_B_dyn(t, h[q] - t.tight);
@@ -521,12 +595,11 @@ __device__ __forceinline__ void step_multi(const EnvT<R> &e, const Theta<R> &t, 
 
 // barrier_dB is defined below (jacobian section)
 template <typename R> __device__ __forceinline__ R barrier_dB(R z, R a, R eps);
-template <typename R, bool GRAD> __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx, R &gy);
 
 // step() that also returns g = B'(h_jac(x+)) grad h(x+), the quantity the barrier row of the augmented jacobian is
 // built from (core/systems/dubins_aug_jac.py:95-129).  The state update is bit-identical to step(): h comes out of
 // the same operation sequence in eval_h<R, true> and eval_h_multi.
-template <typename R>
+template <typename R, int NOBS = -1>
 __device__ __forceinline__ void step_g(const EnvT<R> &e, const Theta<R> &t, State<R> &x, R u0, R u1, R &gx, R &gy) {
     using m = M<R>;
     R s, c;
@@ -536,7 +609,7 @@ __device__ __forceinline__ void step_g(const EnvT<R> &e, const Theta<R> &t, Stat
     const R pyn = m::fma_(dtv, s, x.py);
     const R thn = m::fma_(e.dt, u1, x.th);
     R h, hx, hy;
-    eval_h<R, true>(e, pxn, pyn, h, hx, hy);
+    eval_h<R, true, NOBS>(e, pxn, pyn, h, hx, hy);
     const R Bn = barrier_B_dyn(t, h - t.tight);
     const R dB = barrier_dB(h - t.jac_off, t.a_jac, t.eps_jac);
     gx = dB * hx;

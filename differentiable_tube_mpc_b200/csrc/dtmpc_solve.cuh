@@ -22,14 +22,17 @@
 // at B = 65,536, profiles/r01b), recomputing the winner costs 1/n_alpha more arithmetic and keeps one trajectory per
 // instance.  The alpha = 0 candidate is the current trajectory bit for bit and costs nothing.
 //
-// Slots, not instances, index the big scratch arrays (trajectory, barrier gradients, gains): row r of slot s lives at
-// base[r*B + s].  The commit sweep rewrites the whole trajectory every iteration anyway, so it writes it to the
+// Slots, not instances, index the big scratch arrays (trajectory, barrier gradients, gains), and the arrays are
+// tile-major: 32 consecutive slots form a tile whose rows are contiguous, element (step k, row r) of slot s at
+// base[((s/32 * steps + k) * rows + r) * 32 + s%32].  A warp reads one 256 B segment per row, every address of a sweep
+// is one running pointer plus an immediate (a batch-sized row stride cost ~4 integer instructions per load in 64-bit
+// address arithmetic), and the inputs of a step are one contiguous block.  The commit sweep rewrites the whole trajectory every iteration anyway, so it writes it to the
 // instance's next slot (double-buffered), and the next slot is the instance's rank among the survivors: the running
 // instances always occupy slots 0 .. n_act-1 in ascending instance order.  Every access of a warp is then one full
 // contiguous segment however few instances are left, where an index list over instance-indexed arrays cost up to
 // 2.7x the traffic once a third of the batch had converged (profiles/r01c_iterations.txt).  Small per-instance
-// scalars and the tracked reference stay instance-indexed; the order-preserving compaction keeps those gathers
-// monotone.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
+// scalars and the tracked reference stay instance-indexed (the reference in the same tile-major form); the
+// order-preserving compaction keeps those gathers monotone.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
 #pragma once
 #include "dtmpc_math.cuh"
 
@@ -51,13 +54,13 @@ template <typename R> struct SolveWs {
     int *it;         // [B] completed iterations                         (per instance)
     int *flags;      // [B] bit 0: non-finite in the backward pass       (per instance)
     R *Jcur, *prev, *B0;  // [B] cost of the current trajectory, previous accepted cost, B(h(x0) - tight) (per instance)
-    R *traj[2];      // [4(T+1)+2T+2(T+1)][B] per slot and parity: X, V and g_k = B'(h(x_k)) grad h(x_k), which is what
+    R *traj[2];      // [tiles][T+1][8][32] per slot and parity: x_k (4), u_k (2) and g_k = B'(h(x_k)) grad h(x_k), which is what
                      // the barrier row of the jacobian needs.  g is written by whoever rolls the trajectory out (init,
                      // commit); a separate linearisation kernel and its 8 stored jacobian entries per step made the
                      // backward pass HBM-bound (profiles/r01b)
-    R *gains;        // [10T][B] per slot: K (8 rows per k) then k (2 rows per k)
-    R *ckpt;         // [n_eval][MAX_SEG-1][5][B] per slot: state of every candidate at the segment boundaries
-    R *ref;          // [3(T+1)+2T][B] tracked reference (auxiliary OCP)  (per instance)
+    R *gains;        // [tiles][T][10][32] per slot: K_k (8) then k_k (2)
+    R *ckpt;         // [tiles][n_eval][MAX_SEG-1][5][32] per slot: state of every candidate at the segment boundaries
+    R *ref;          // [tiles][T+1][5][32] tracked reference x (3), u (2) of the auxiliary OCP  (per instance)
 };
 
 template <typename R> struct SolveParams {
@@ -80,10 +83,16 @@ constexpr int MAX_SEG = 5;
 
 constexpr int LS_BLOCK = 128;
 
-__host__ __device__ inline long long traj_rows(int T) { return 4LL * (T + 1) + 2LL * T + 2LL * (T + 1); }
-__host__ __device__ inline long long traj_v_row(int T) { return 4LL * (T + 1); }
-__host__ __device__ inline long long traj_g_row(int T) { return 4LL * (T + 1) + 2LL * T; }
-__host__ __device__ inline long long ref_rows(int T) { return 3LL * (T + 1) + 2LL * T; }
+// rows per step of the tile-major arrays, and the element offset of (slot or instance) s in an array of `rows` rows
+constexpr int TR = 8;    // trajectory: x 0-3, u 4-5, g 6-7
+constexpr int GR = 10;   // gains: K 0-7 (row-major 2x4), k 8-9
+constexpr int RR = 5;    // reference: x 0-2, u 3-4
+constexpr int CR = 5;    // checkpoint: px, py, th, b, Bc
+__host__ __device__ inline long long traj_rows(int T) { return (long long)TR * (T + 1); }
+__host__ __device__ inline long long gain_rows(int T) { return (long long)GR * T; }
+__host__ __device__ inline long long ref_rows(int T) { return (long long)RR * (T + 1); }
+__host__ __device__ inline long long tile_off(long long s, long long rows) { return (s >> 5) * rows * 32 + (s & 31); }
+#define EL(k, rows, r) ((((k) * (rows)) + (r)) * 32)  // element (step k, row r) relative to the slot's tile pointer
 
 template <typename R> struct RefPt { R x0, x1, x2, u0, u1; };
 
@@ -107,16 +116,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename R>
-__device__ __forceinline__ void ref_at(const SolveParams<R> &P, long long i, int k, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
-    if (P.use_ref) {
-        const long long S = P.B;
-        const int T = P.ocp.T;
-        r.x0 = P.ws.ref[(3LL * k + 0) * S + i];
-        r.x1 = P.ws.ref[(3LL * k + 1) * S + i];
-        r.x2 = P.ws.ref[(3LL * k + 2) * S + i];
+__device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *ref_i, int k, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
+    if (P.use_ref) {  // ref_i = ws.ref + tile_off(i, ref_rows(T))
+        r.x0 = ref_i[EL(k, RR, 0)];
+        r.x1 = ref_i[EL(k, RR, 1)];
+        r.x2 = ref_i[EL(k, RR, 2)];
         if (with_u) {
-            r.u0 = P.ws.ref[(3LL * (T + 1) + 2LL * k + 0) * S + i];
-            r.u1 = P.ws.ref[(3LL * (T + 1) + 2LL * k + 1) * S + i];
+            r.u0 = ref_i[EL(k, RR, 3)];
+            r.u1 = ref_i[EL(k, RR, 4)];
         } else {
             r.u0 = R(0); r.u1 = R(0);
         }
@@ -137,14 +144,16 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     if (i >= P.B) return;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
-    const long long S = P.B;
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+    R *ref_i = P.ws.ref + tile_off(i, ref_rows(T));
     if (P.ref_from_io) {
         const R *xr = P.io.Xref + i * (3LL * (T + 1));
         const R *ur = P.io.Uref + i * (2LL * T);
-        for (int r = 0; r < 3 * (T + 1); ++r) P.ws.ref[(long long)r * S + i] = xr[r];
-        for (int r = 0; r < 2 * T; ++r) P.ws.ref[(3LL * (T + 1) + r) * S + i] = ur[r];
+        for (int k = 0; k <= T; ++k)
+            for (int c = 0; c < 3; ++c) ref_i[EL(k, RR, c)] = xr[3 * k + c];
+        for (int k = 0; k < T; ++k)
+            for (int c = 0; c < 2; ++c) ref_i[EL(k, RR, 3 + c)] = ur[2 * k + c];
     }
     R t0 = R(0), t1 = R(0), t2 = R(0);
     if (!P.use_ref) {
@@ -155,36 +164,34 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     State<R> x{x0p[0], x0p[1], x0p[2], x0p[3], R(0)};
     x.Bc = barrier_of_state(E, th, x.px, x.py);
     P.ws.B0[i] = x.Bc;
-    R *X = P.ws.traj[0] + i;                    // slot i of parity 0
-    R *V = X + traj_v_row(T) * S;
-    X[0 * S] = x.px; X[1 * S] = x.py; X[2 * S] = x.th; X[3 * S] = x.b;
-    R *G = X + traj_g_row(T) * S;
+    R *X = P.ws.traj[0] + tile_off(i, traj_rows(T));  // slot i of parity 0
+    X[EL(0, TR, 0)] = x.px; X[EL(0, TR, 1)] = x.py; X[EL(0, TR, 2)] = x.th; X[EL(0, TR, 3)] = x.b;
     {
         R g0x, g0y, h0;
         barrier_grad(E, th, x.px, x.py, g0x, g0y, h0);
-        G[0 * S] = g0x; G[1 * S] = g0y;
+        X[EL(0, TR, 6)] = g0x; X[EL(0, TR, 7)] = g0y;
     }
     const R *vp = P.io.V_init + i * (2LL * T);
     R J = R(0);
     for (int k = 0; k < T; ++k) {
         R u0 = vp[2 * k], u1 = vp[2 * k + 1];
         clamp_u(E, u0, u1);
-        V[(2LL * k) * S] = u0;
-        V[(2LL * k + 1) * S] = u1;
+        X[EL(k, TR, 4)] = u0;
+        X[EL(k, TR, 5)] = u1;
         RefPt<R> r;
-        ref_at(P, i, k, true, t0, t1, t2, r);
+        ref_at(P, ref_i, k, true, t0, t1, t2, r);
         J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
         R gx, gy;
         step_g(E, th, x, u0, u1, gx, gy);
-        X[(4LL * (k + 1) + 0) * S] = x.px;
-        X[(4LL * (k + 1) + 1) * S] = x.py;
-        X[(4LL * (k + 1) + 2) * S] = x.th;
-        X[(4LL * (k + 1) + 3) * S] = x.b;
-        G[(2LL * (k + 1) + 0) * S] = gx;
-        G[(2LL * (k + 1) + 1) * S] = gy;
+        X[EL(k + 1, TR, 0)] = x.px;
+        X[EL(k + 1, TR, 1)] = x.py;
+        X[EL(k + 1, TR, 2)] = x.th;
+        X[EL(k + 1, TR, 3)] = x.b;
+        X[EL(k + 1, TR, 6)] = gx;
+        X[EL(k + 1, TR, 7)] = gy;
     }
     RefPt<R> r;
-    ref_at(P, i, T, false, t0, t1, t2, r);
+    ref_at(P, ref_i, T, false, t0, t1, t2, r);
     J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
     P.ws.Jcur[i] = J;
     P.ws.prev[i] = R(0);
@@ -213,7 +220,6 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
     if (j >= n_act) return;
     const long long i = P.ws.list[P.parity][j];
-    const long long S = P.B;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
     Theta<R> th;
@@ -223,19 +229,17 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
-    const R *X = P.ws.traj[P.parity] + j;
-    const R *V = X + traj_v_row(T) * S;
-    const R *G = X + traj_g_row(T) * S;
-    R *GK = P.ws.gains + j;
-    R *Gk = GK + 8LL * T * S;
+    const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
+    R *GK = P.ws.gains + tile_off(j, gain_rows(T));
+    const R *ref_i = P.ws.ref + tile_off(i, ref_rows(T));
     const R reg = P.ocp.reg;
 
     R Vx0, Vx1, Vx2, Vx3;
     R V00, V01, V02, V03, V10, V11, V12, V13, V20, V21, V22, V23, V30, V31, V32, V33;
     {
-        const R px = X[(4LL * T + 0) * S], py = X[(4LL * T + 1) * S], pt = X[(4LL * T + 2) * S], pb = X[(4LL * T + 3) * S];
+        const R px = X[EL(T, TR, 0)], py = X[EL(T, TR, 1)], pt = X[EL(T, TR, 2)], pb = X[EL(T, TR, 3)];
         RefPt<R> r;
-        ref_at(P, i, T, false, t0, t1, t2, r);
+        ref_at(P, ref_i, T, false, t0, t1, t2, r);
         // terminal derivatives: core/cost_derivs.py:132-146 + barrier entries core/tube_mpc.py:839-841
         Vx0 = (R(2) * th.Qf0) * (px - r.x0);
         Vx1 = (R(2) * th.Qf1) * (py - r.x1);
@@ -254,12 +258,12 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         R gx, gy;
     };
     auto load_step = [&](int k, RicIn &q) {
-        q.px = X[(4LL * k + 0) * S]; q.py = X[(4LL * k + 1) * S]; q.pt = X[(4LL * k + 2) * S]; q.pb = X[(4LL * k + 3) * S];
-        q.u0 = V[(2LL * k) * S]; q.u1 = V[(2LL * k + 1) * S];
-        ref_at(P, i, k, true, t0, t1, t2, q.r);
-        q.gx = G[(2LL * k + 0) * S]; q.gy = G[(2LL * k + 1) * S];
+        q.px = X[EL(k, TR, 0)]; q.py = X[EL(k, TR, 1)]; q.pt = X[EL(k, TR, 2)]; q.pb = X[EL(k, TR, 3)];
+        q.u0 = X[EL(k, TR, 4)]; q.u1 = X[EL(k, TR, 5)];
+        ref_at(P, ref_i, k, true, t0, t1, t2, q.r);
+        q.gx = X[EL(k, TR, 6)]; q.gy = X[EL(k, TR, 7)];
     };
-    R gnx = G[(2LL * T + 0) * S], gny = G[(2LL * T + 1) * S];  // g at x_T, then carried backwards
+    R gnx = X[EL(T, TR, 6)], gny = X[EL(T, TR, 7)];  // g at x_T, then carried backwards
     RicIn in;
 #if DTMPC_RIC_PREFETCH
     load_step(T - 1, in);
@@ -271,18 +275,6 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 #else
         load_step(k, in);
         nx = in;
-#endif
-#if DTMPC_L2_PREFETCH > 0
-        if (k - 1 - DTMPC_L2_PREFETCH >= 0) {
-            const int kp = k - 1 - DTMPC_L2_PREFETCH;
-            for (int c = 0; c < 4; ++c) prefetch_l2(X + (4LL * kp + c) * S);
-            for (int c = 0; c < 2; ++c) prefetch_l2(V + (2LL * kp + c) * S);
-            for (int c = 0; c < 2; ++c) prefetch_l2(G + (2LL * kp + c) * S);
-            if (P.use_ref) {
-                for (int c = 0; c < 3; ++c) prefetch_l2(P.ws.ref + (3LL * kp + c) * S + i);
-                for (int c = 0; c < 2; ++c) prefetch_l2(P.ws.ref + (3LL * (T + 1) + 2LL * kp + c) * S + i);
-            }
-        }
 #endif
         const R px = in.px, py = in.py, pt = in.pt, pb = in.pb, u0 = in.u0, u1 = in.u1;
         const RefPt<R> r = in.r;
@@ -349,11 +341,11 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         K10 = -K10; K11 = -K11; K12 = -K12; K13 = -K13;
         k0 = -k0; k1 = -k1;
         {
-            R *o = GK + (8LL * k) * S;
-            o[0 * S] = K00; o[1 * S] = K01; o[2 * S] = K02; o[3 * S] = K03;
-            o[4 * S] = K10; o[5 * S] = K11; o[6 * S] = K12; o[7 * S] = K13;
-            Gk[(2LL * k) * S] = k0;
-            Gk[(2LL * k + 1) * S] = k1;
+            R *o = GK + EL(k, GR, 0);
+            o[0 * 32] = K00; o[1 * 32] = K01; o[2 * 32] = K02; o[3 * 32] = K03;
+            o[4 * 32] = K10; o[5 * 32] = K11; o[6 * 32] = K12; o[7 * 32] = K13;
+            o[8 * 32] = k0;
+            o[9 * 32] = k1;
         }
         // V_x = Q_x + K^T Q_uu k + K^T Q_u + Q_xu k   (un-regularised Q_uu, core/ddp.py:251)
         const R s0 = m::fma_(Quu01, k1, Quu00 * k0) + Qu0;
@@ -396,7 +388,7 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 #endif
 constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 
-template <typename R, int NC>
+template <typename R, int NC, int NOBS = -1>
 __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     __shared__ R sJ[DTMPC_MAX_ALPHAS * 32];
@@ -406,7 +398,6 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
     const bool live = (int)blockIdx.x * 32 + lane < n_act;
     const int j = live ? blockIdx.x * 32 + lane : n_act - 1;  // idle lanes shadow the last slot (they reach the barrier)
     const long long i = P.ws.list[P.parity][j];
-    const long long S = P.B;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
     int a_idx[NC];
@@ -426,15 +417,15 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
-    const R *X = P.ws.traj[P.parity] + j;
-    const R *V = X + traj_v_row(T) * S;
-    const R *GK = P.ws.gains + j;
-    const R *Gk = GK + 8LL * T * S;
+    const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
+    const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
+    const R *ref_i = P.ws.ref + tile_off(i, ref_rows(T));
+    R *CK = P.ws.ckpt + tile_off(j, (long long)CR * (MAX_SEG - 1) * P.n_eval);
 
     State<R> x[NC];
     R J[NC];
     {
-        const State<R> x0{X[0 * S], X[1 * S], X[2 * S], X[3 * S], P.ws.B0[i]};
+        const State<R> x0{X[EL(0, TR, 0)], X[EL(0, TR, 1)], X[EL(0, TR, 2)], X[EL(0, TR, 3)], P.ws.B0[i]};
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
             x[q] = x0;
@@ -448,21 +439,21 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
 #pragma unroll
                 for (int q = 0; q < NC; ++q) {
                     if (!valid[q]) continue;
-                    R *c = P.ws.ckpt + ((long long)((threadIdx.y * NC + q) * (MAX_SEG - 1) + seg) * 5) * S + j;
-                    c[0 * S] = x[q].px; c[1 * S] = x[q].py; c[2 * S] = x[q].th; c[3 * S] = x[q].b; c[4 * S] = x[q].Bc;
+                    R *c = CK + EL((threadIdx.y * NC + q) * (MAX_SEG - 1) + seg, CR, 0);
+                    c[0 * 32] = x[q].px; c[1 * 32] = x[q].py; c[2 * 32] = x[q].th; c[3 * 32] = x[q].b; c[4 * 32] = x[q].Bc;
                 }
             }
             k_ck += P.seg_len;
             ++seg;
         }
-        const R X0 = X[(4LL * k + 0) * S], X1 = X[(4LL * k + 1) * S], X2 = X[(4LL * k + 2) * S], X3 = X[(4LL * k + 3) * S];
-        const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
-        const R *o = GK + (8LL * k) * S;
-        const R K00 = o[0 * S], K01 = o[1 * S], K02 = o[2 * S], K03 = o[3 * S];
-        const R K10 = o[4 * S], K11 = o[5 * S], K12 = o[6 * S], K13 = o[7 * S];
-        const R k0 = Gk[(2LL * k) * S], k1 = Gk[(2LL * k + 1) * S];
+        const R X0 = X[EL(k, TR, 0)], X1 = X[EL(k, TR, 1)], X2 = X[EL(k, TR, 2)], X3 = X[EL(k, TR, 3)];
+        const R v0 = X[EL(k, TR, 4)], v1 = X[EL(k, TR, 5)];
+        const R *o = GK + EL(k, GR, 0);
+        const R K00 = o[0 * 32], K01 = o[1 * 32], K02 = o[2 * 32], K03 = o[3 * 32];
+        const R K10 = o[4 * 32], K11 = o[5 * 32], K12 = o[6 * 32], K13 = o[7 * 32];
+        const R k0 = o[8 * 32], k1 = o[9 * 32];
         RefPt<R> r;
-        ref_at(P, i, k, true, t0, t1, t2, r);
+        ref_at(P, ref_i, k, true, t0, t1, t2, r);
         R u0[NC], u1[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
@@ -475,10 +466,10 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
             clamp_u(E, u0[q], u1[q]);
             J[q] += stage_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, u0[q], u1[q], r.x0, r.x1, r.x2, r.u0, r.u1);
         }
-        step_multi<R, NC>(E, th, x, u0, u1);
+        step_multi<R, NC, NOBS>(E, th, x, u0, u1);
     }
     RefPt<R> r;
-    ref_at(P, i, T, false, t0, t1, t2, r);
+    ref_at(P, ref_i, T, false, t0, t1, t2, r);
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         J[q] += terminal_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, r.x0, r.x1, r.x2);
@@ -551,7 +542,8 @@ __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 __device__ __forceinline__ void st2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
 
-template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_constant__ SolveParams<R> P) {
+template <typename R, int NOBS = -1>
+__global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     __shared__ int s_part[MAX_SEG];
     const int n_act = P.ws.counts[P.parity];
@@ -581,52 +573,47 @@ template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kern
     const R al = (d & DEC_BAD) ? R(0) : P.ocp.alphas[d & 0xff];
     const bool copy = al == R(0);  // the current trajectory stays
 
-    const long long S = P.B;
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
     const int k_lo = seg * P.seg_len, k_hi = min(T, k_lo + P.seg_len);
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
-    const R *X = P.ws.traj[P.parity] + j;
-    const R *V = X + traj_v_row(T) * S;
-    const R *G = X + traj_g_row(T) * S;
-    const R *GK = P.ws.gains + j;
-    const R *Gk = GK + 8LL * T * S;
+    const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
+    const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
     // destinations: next slot (running) or the result tensors (stopping)
-    R *Xn = P.ws.traj[P.parity ^ 1] + jn;
-    R *Vn = Xn + traj_v_row(T) * S;
-    R *Gn = Xn + traj_g_row(T) * S;
+    R *Xn = P.ws.traj[P.parity ^ 1] + tile_off(jn, traj_rows(T));
     R *Xo = P.io.X + i * (4LL * (T + 1));
     R *Vo = P.io.V + i * (2LL * T);
     R *Ko = P.io.K ? P.io.K + i * (8LL * T) : nullptr;
     R *ko = P.io.kff ? P.io.kff + i * (2LL * T) : nullptr;
-    R *Ro = P.write_ref ? P.ws.ref + i : nullptr;
+    R *Ro = P.write_ref ? P.ws.ref + tile_off(i, ref_rows(T)) : nullptr;
 
     // state at the head of the segment: x_0, or the winner's checkpoint; and the old trajectory's state there
-    R X0 = X[(4LL * k_lo + 0) * S], X1 = X[(4LL * k_lo + 1) * S], X2 = X[(4LL * k_lo + 2) * S], X3 = X[(4LL * k_lo + 3) * S];
+    R X0 = X[EL(k_lo, TR, 0)], X1 = X[EL(k_lo, TR, 1)], X2 = X[EL(k_lo, TR, 2)], X3 = X[EL(k_lo, TR, 3)];
     State<R> x{X0, X1, X2, X3, R(0)};
     if (seg == 0) {
         x.Bc = P.ws.B0[i];
         if (keep) {
-            Xn[0 * S] = X0; Xn[1 * S] = X1; Xn[2 * S] = X2; Xn[3 * S] = X3;
-            Gn[0 * S] = G[0 * S]; Gn[1 * S] = G[1 * S];
+            Xn[EL(0, TR, 0)] = X0; Xn[EL(0, TR, 1)] = X1; Xn[EL(0, TR, 2)] = X2; Xn[EL(0, TR, 3)] = X3;
+            Xn[EL(0, TR, 6)] = X[EL(0, TR, 6)]; Xn[EL(0, TR, 7)] = X[EL(0, TR, 7)];
         } else {
             st4(Xo, X0, X1, X2, X3);
-            if (Ro) { Ro[0 * S] = X0; Ro[1 * S] = X1; Ro[2 * S] = X2; }
+            if (Ro) { Ro[EL(0, RR, 0)] = X0; Ro[EL(0, RR, 1)] = X1; Ro[EL(0, RR, 2)] = X2; }
             if (P.io.iters) P.io.iters[i] = P.ws.it[i];
         }
     } else if (!copy) {
-        const R *c = P.ws.ckpt + ((long long)(P.eval_pos[d & 0xff] * (MAX_SEG - 1) + (seg - 1)) * 5) * S + j;
-        x.px = c[0 * S]; x.py = c[1 * S]; x.th = c[2 * S]; x.b = c[3 * S]; x.Bc = c[4 * S];
+        const R *c = P.ws.ckpt + tile_off(j, (long long)CR * (MAX_SEG - 1) * P.n_eval) +
+                     EL(P.eval_pos[d & 0xff] * (MAX_SEG - 1) + (seg - 1), CR, 0);
+        x.px = c[0 * 32]; x.py = c[1 * 32]; x.th = c[2 * 32]; x.b = c[3 * 32]; x.Bc = c[4 * 32];
     }
     for (int k = k_lo; k < k_hi; ++k) {
-        const R v0 = V[(2LL * k) * S], v1 = V[(2LL * k + 1) * S];
-        const R *o = GK + (8LL * k) * S;
-        const R K00 = o[0 * S], K01 = o[1 * S], K02 = o[2 * S], K03 = o[3 * S];
-        const R K10 = o[4 * S], K11 = o[5 * S], K12 = o[6 * S], K13 = o[7 * S];
-        const R k0 = Gk[(2LL * k) * S], k1 = Gk[(2LL * k + 1) * S];
-        const R N0 = X[(4LL * (k + 1) + 0) * S], N1 = X[(4LL * (k + 1) + 1) * S];
-        const R N2 = X[(4LL * (k + 1) + 2) * S], N3 = X[(4LL * (k + 1) + 3) * S];
+        const R v0 = X[EL(k, TR, 4)], v1 = X[EL(k, TR, 5)];
+        const R *o = GK + EL(k, GR, 0);
+        const R K00 = o[0 * 32], K01 = o[1 * 32], K02 = o[2 * 32], K03 = o[3 * 32];
+        const R K10 = o[4 * 32], K11 = o[5 * 32], K12 = o[6 * 32], K13 = o[7 * 32];
+        const R k0 = o[8 * 32], k1 = o[9 * 32];
+        const R N0 = X[EL(k + 1, TR, 0)], N1 = X[EL(k + 1, TR, 1)];
+        const R N2 = X[EL(k + 1, TR, 2)], N3 = X[EL(k + 1, TR, 3)];
         R u0 = v0, u1 = v1, gx, gy;
         if (!copy) {
             const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
@@ -635,21 +622,21 @@ template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kern
             u0 = m::fma_(al, du0, v0);
             u1 = m::fma_(al, du1, v1);
             clamp_u(E, u0, u1);
-            step_g(E, th, x, u0, u1, gx, gy);
+            step_g<R, NOBS>(E, th, x, u0, u1, gx, gy);
         } else {
             x.px = N0; x.py = N1; x.th = N2; x.b = N3;
-            gx = G[(2LL * (k + 1) + 0) * S];
-            gy = G[(2LL * (k + 1) + 1) * S];
+            gx = X[EL(k + 1, TR, 6)];
+            gy = X[EL(k + 1, TR, 7)];
         }
         if (keep) {
-            Vn[(2LL * k) * S] = u0;
-            Vn[(2LL * k + 1) * S] = u1;
-            Xn[(4LL * (k + 1) + 0) * S] = x.px;
-            Xn[(4LL * (k + 1) + 1) * S] = x.py;
-            Xn[(4LL * (k + 1) + 2) * S] = x.th;
-            Xn[(4LL * (k + 1) + 3) * S] = x.b;
-            Gn[(2LL * (k + 1) + 0) * S] = gx;
-            Gn[(2LL * (k + 1) + 1) * S] = gy;
+            Xn[EL(k, TR, 4)] = u0;
+            Xn[EL(k, TR, 5)] = u1;
+            Xn[EL(k + 1, TR, 0)] = x.px;
+            Xn[EL(k + 1, TR, 1)] = x.py;
+            Xn[EL(k + 1, TR, 2)] = x.th;
+            Xn[EL(k + 1, TR, 3)] = x.b;
+            Xn[EL(k + 1, TR, 6)] = gx;
+            Xn[EL(k + 1, TR, 7)] = gy;
         } else {
             st2(Vo + 2 * k, u0, u1);
             st4(Xo + 4 * (k + 1), x.px, x.py, x.th, x.b);
@@ -659,11 +646,11 @@ template <typename R> __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kern
             }
             if (ko) st2(ko + 2 * k, k0, k1);
             if (Ro) {
-                Ro[(3LL * (k + 1) + 0) * S] = x.px;
-                Ro[(3LL * (k + 1) + 1) * S] = x.py;
-                Ro[(3LL * (k + 1) + 2) * S] = x.th;
-                Ro[(3LL * (T + 1) + 2LL * k + 0) * S] = u0;
-                Ro[(3LL * (T + 1) + 2LL * k + 1) * S] = u1;
+                Ro[EL(k + 1, RR, 0)] = x.px;
+                Ro[EL(k + 1, RR, 1)] = x.py;
+                Ro[EL(k + 1, RR, 2)] = x.th;
+                Ro[EL(k, RR, 3)] = u0;
+                Ro[EL(k, RR, 4)] = u1;
             }
         }
         X0 = N0; X1 = N1; X2 = N2; X3 = N3;

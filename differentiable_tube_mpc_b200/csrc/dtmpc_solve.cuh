@@ -116,14 +116,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename R>
-__device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *ref_i, int k, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
-    if (P.use_ref) {  // ref_i = ws.ref + tile_off(i, ref_rows(T))
-        r.x0 = ref_i[EL(k, RR, 0)];
-        r.x1 = ref_i[EL(k, RR, 1)];
-        r.x2 = ref_i[EL(k, RR, 2)];
+__device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *rk, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
+    if (P.use_ref) {  // rk = ws.ref + tile_off(i, ref_rows(T)) + EL(k, RR, 0): the reference of step k
+        r.x0 = rk[0 * 32];
+        r.x1 = rk[1 * 32];
+        r.x2 = rk[2 * 32];
         if (with_u) {
-            r.u0 = ref_i[EL(k, RR, 3)];
-            r.u1 = ref_i[EL(k, RR, 4)];
+            r.u0 = rk[3 * 32];
+            r.u1 = rk[4 * 32];
         } else {
             r.u0 = R(0); r.u1 = R(0);
         }
@@ -179,7 +179,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
         X[EL(k, TR, 4)] = u0;
         X[EL(k, TR, 5)] = u1;
         RefPt<R> r;
-        ref_at(P, ref_i, k, true, t0, t1, t2, r);
+        ref_at(P, ref_i + EL(k, RR, 0), true, t0, t1, t2, r);
         J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
         R gx, gy;
         step_g(E, th, x, u0, u1, gx, gy);
@@ -191,7 +191,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
         X[EL(k + 1, TR, 7)] = gy;
     }
     RefPt<R> r;
-    ref_at(P, ref_i, T, false, t0, t1, t2, r);
+    ref_at(P, ref_i + EL(T, RR, 0), false, t0, t1, t2, r);
     J += terminal_cost(th, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
     P.ws.Jcur[i] = J;
     P.ws.prev[i] = R(0);
@@ -239,7 +239,7 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     {
         const R px = X[EL(T, TR, 0)], py = X[EL(T, TR, 1)], pt = X[EL(T, TR, 2)], pb = X[EL(T, TR, 3)];
         RefPt<R> r;
-        ref_at(P, ref_i, T, false, t0, t1, t2, r);
+        ref_at(P, ref_i + EL(T, RR, 0), false, t0, t1, t2, r);
         // terminal derivatives: core/cost_derivs.py:132-146 + barrier entries core/tube_mpc.py:839-841
         Vx0 = (R(2) * th.Qf0) * (px - r.x0);
         Vx1 = (R(2) * th.Qf1) * (py - r.x1);
@@ -258,10 +258,11 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         R gx, gy;
     };
     auto load_step = [&](int k, RicIn &q) {
-        q.px = X[EL(k, TR, 0)]; q.py = X[EL(k, TR, 1)]; q.pt = X[EL(k, TR, 2)]; q.pb = X[EL(k, TR, 3)];
-        q.u0 = X[EL(k, TR, 4)]; q.u1 = X[EL(k, TR, 5)];
-        ref_at(P, ref_i, k, true, t0, t1, t2, q.r);
-        q.gx = X[EL(k, TR, 6)]; q.gy = X[EL(k, TR, 7)];
+        const R *xk = X + EL(k, TR, 0);
+        q.px = xk[0 * 32]; q.py = xk[1 * 32]; q.pt = xk[2 * 32]; q.pb = xk[3 * 32];
+        q.u0 = xk[4 * 32]; q.u1 = xk[5 * 32];
+        ref_at(P, ref_i + EL(k, RR, 0), true, t0, t1, t2, q.r);
+        q.gx = xk[6 * 32]; q.gy = xk[7 * 32];
     };
     R gnx = X[EL(T, TR, 6)], gny = X[EL(T, TR, 7)];  // g at x_T, then carried backwards
     RicIn in;
@@ -433,6 +434,7 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         }
     }
     int k_ck = P.seg_len, seg = 0;  // next segment boundary
+    const R *xp = X, *gp = GK, *rp = ref_i;
     for (int k = 0; k < T; ++k) {
         if (k == k_ck) {  // the commit sweep restarts the winner from here (uniform branch)
             if (live) {
@@ -446,14 +448,16 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
             k_ck += P.seg_len;
             ++seg;
         }
-        const R X0 = X[EL(k, TR, 0)], X1 = X[EL(k, TR, 1)], X2 = X[EL(k, TR, 2)], X3 = X[EL(k, TR, 3)];
-        const R v0 = X[EL(k, TR, 4)], v1 = X[EL(k, TR, 5)];
-        const R *o = GK + EL(k, GR, 0);
-        const R K00 = o[0 * 32], K01 = o[1 * 32], K02 = o[2 * 32], K03 = o[3 * 32];
-        const R K10 = o[4 * 32], K11 = o[5 * 32], K12 = o[6 * 32], K13 = o[7 * 32];
-        const R k0 = o[8 * 32], k1 = o[9 * 32];
+        const R X0 = xp[0 * 32], X1 = xp[1 * 32], X2 = xp[2 * 32], X3 = xp[3 * 32];
+        const R v0 = xp[4 * 32], v1 = xp[5 * 32];
+        const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
+        const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
+        const R k0 = gp[8 * 32], k1 = gp[9 * 32];
         RefPt<R> r;
-        ref_at(P, ref_i, k, true, t0, t1, t2, r);
+        ref_at(P, rp, true, t0, t1, t2, r);
+        xp += TR * 32;  // one running pointer per stream: every load is pointer + immediate
+        gp += GR * 32;
+        rp += RR * 32;
         R u0[NC], u1[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
@@ -469,7 +473,7 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         step_multi<R, NC, NOBS>(E, th, x, u0, u1);
     }
     RefPt<R> r;
-    ref_at(P, ref_i, T, false, t0, t1, t2, r);
+    ref_at(P, rp, false, t0, t1, t2, r);
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         J[q] += terminal_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, r.x0, r.x1, r.x2);
@@ -606,14 +610,15 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
                      EL(P.eval_pos[d & 0xff] * (MAX_SEG - 1) + (seg - 1), CR, 0);
         x.px = c[0 * 32]; x.py = c[1 * 32]; x.th = c[2 * 32]; x.b = c[3 * 32]; x.Bc = c[4 * 32];
     }
+    const R *xp = X + EL(k_lo, TR, 0), *gp = GK + EL(k_lo, GR, 0);
+    R *xn = Xn + EL(k_lo, TR, 0);
     for (int k = k_lo; k < k_hi; ++k) {
-        const R v0 = X[EL(k, TR, 4)], v1 = X[EL(k, TR, 5)];
-        const R *o = GK + EL(k, GR, 0);
-        const R K00 = o[0 * 32], K01 = o[1 * 32], K02 = o[2 * 32], K03 = o[3 * 32];
-        const R K10 = o[4 * 32], K11 = o[5 * 32], K12 = o[6 * 32], K13 = o[7 * 32];
-        const R k0 = o[8 * 32], k1 = o[9 * 32];
-        const R N0 = X[EL(k + 1, TR, 0)], N1 = X[EL(k + 1, TR, 1)];
-        const R N2 = X[EL(k + 1, TR, 2)], N3 = X[EL(k + 1, TR, 3)];
+        const R v0 = xp[4 * 32], v1 = xp[5 * 32];
+        const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
+        const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
+        const R k0 = gp[8 * 32], k1 = gp[9 * 32];
+        const R N0 = xp[(TR + 0) * 32], N1 = xp[(TR + 1) * 32];
+        const R N2 = xp[(TR + 2) * 32], N3 = xp[(TR + 3) * 32];
         R u0 = v0, u1 = v1, gx, gy;
         if (!copy) {
             const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
@@ -625,18 +630,21 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
             step_g<R, NOBS>(E, th, x, u0, u1, gx, gy);
         } else {
             x.px = N0; x.py = N1; x.th = N2; x.b = N3;
-            gx = X[EL(k + 1, TR, 6)];
-            gy = X[EL(k + 1, TR, 7)];
+            gx = xp[(TR + 6) * 32];
+            gy = xp[(TR + 7) * 32];
         }
+        xp += TR * 32;
+        gp += GR * 32;
         if (keep) {
-            Xn[EL(k, TR, 4)] = u0;
-            Xn[EL(k, TR, 5)] = u1;
-            Xn[EL(k + 1, TR, 0)] = x.px;
-            Xn[EL(k + 1, TR, 1)] = x.py;
-            Xn[EL(k + 1, TR, 2)] = x.th;
-            Xn[EL(k + 1, TR, 3)] = x.b;
-            Xn[EL(k + 1, TR, 6)] = gx;
-            Xn[EL(k + 1, TR, 7)] = gy;
+            xn[4 * 32] = u0;
+            xn[5 * 32] = u1;
+            xn[(TR + 0) * 32] = x.px;
+            xn[(TR + 1) * 32] = x.py;
+            xn[(TR + 2) * 32] = x.th;
+            xn[(TR + 3) * 32] = x.b;
+            xn[(TR + 6) * 32] = gx;
+            xn[(TR + 7) * 32] = gy;
+            xn += TR * 32;
         } else {
             st2(Vo + 2 * k, u0, u1);
             st4(Xo + 4 * (k + 1), x.px, x.py, x.th, x.b);

@@ -78,7 +78,7 @@ class SensIO(C.Structure):
 # every symbol include/dtmpc.h declares (tests/test_abi.py checks the header against this list)
 _PER_DTYPE = ("ilqr_solve", "tube_solve", "sensitivity", "ift_accumulate", "reduce_columns", "rollout", "primitives",
               "plant_step")
-EXPORTS = ["dtmpc_abi_version", "dtmpc_last_error", "dtmpc_solve_workspace_bytes", "dtmpc_sens_workspace_bytes",
+EXPORTS = ["dtmpc_abi_version", "dtmpc_last_error", "dtmpc_kernel_launches", "dtmpc_solve_workspace_bytes", "dtmpc_sens_workspace_bytes",
            "dtmpc_reduce_workspace_bytes", "dtmpc_measure_fp64_peak_tflops", "dtmpc_measure_fp32_peak_tflops"] + [
     f"dtmpc_{n}_{s}" for n in _PER_DTYPE for s in ("f64", "f32")]
 
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
     pe, po = C.POINTER(Env), C.POINTER(Ocp)
     L.dtmpc_abi_version.restype = C.c_int
     L.dtmpc_last_error.restype = C.c_char_p
+    L.dtmpc_kernel_launches.restype = C.c_uint64
     L.dtmpc_solve_workspace_bytes.restype = sz
     L.dtmpc_solve_workspace_bytes.argtypes = [i32, i64, i32, i32]
     L.dtmpc_sens_workspace_bytes.restype = sz

@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -18,6 +19,8 @@ using namespace dtmpc;
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_kernel_launches{0};  // every kernel this library enqueues (dtmpc_kernel_launches)
+inline void count_launches(unsigned long long n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int fail(int code, const char *msg) {
     snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -181,6 +184,7 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
         else commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
         P.parity ^= 1;
     }
+    count_launches(1ull + 3ull * (unsigned long long)P.ocp.max_iter);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "iLQR kernel launch");
     return DTMPC_OK;
@@ -372,6 +376,7 @@ int sens_impl(const dtmpc_env *env, const dtmpc_ocp *ocp, long long B, const dtm
         P.ws = (R *)ws;
         sens_kernel<R><<<grid, SENS_BLOCK, 0, st>>>(P);
     }
+    count_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "sensitivity kernel launch");
     return DTMPC_OK;
@@ -435,6 +440,7 @@ int reduce_impl(const void *g, long long B, int ncols, void *out, void *ws, size
     const long long nb = B > 0 ? (B + RED_ROWS - 1) / RED_ROWS : 0;
     if (nb > 0) reduce_partial_kernel<R><<<(unsigned)nb, RED_BLOCK, 0, st>>>((const R *)g, B, ncols, (R *)ws);
     reduce_final_kernel<R><<<1, RED_BLOCK, 0, st>>>((const R *)ws, nb, ncols, (R *)out);
+    count_launches(nb > 0 ? 2 : 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
     return DTMPC_OK;
@@ -581,11 +587,13 @@ template <typename R> double peak_impl(int iters, void *stream) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    count_launches(1);
     fma_peak_kernel<R><<<grid, block, 0, st>>>(buf, iters);  // warm-up
     double best = 0.0;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0, st);
         fma_peak_kernel<R><<<grid, block, 0, st>>>(buf, iters);
+        count_launches(1);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -613,6 +621,7 @@ size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_
     if (elem_size == 4) return carve_solve_ws<float>(nullptr, T, B, n_alpha, nullptr) + chunked_ws_bytes_slack();
     return 0;
 }
+uint64_t dtmpc_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size) {
     if (T < 1 || B < 0) return 0;
     return (size_t)sens_ws_rows(T) * (size_t)B * (size_t)elem_size + 256;
@@ -654,6 +663,7 @@ size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size)
         OcpT<R> O;                                                                                                    \
         convert_env(*env, E);                                                                                         \
         convert_ocp(*ocp, O);                                                                                         \
+        count_launches(1);                                                                                            \
         rollout_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                             \
             E, O, B, (const R *)x0, (const R *)V, (const R *)theta, theta_stride, (R *)X);                            \
         cudaError_t e = cudaGetLastError();                                                                           \
@@ -670,6 +680,7 @@ size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size)
         OcpT<R> O;                                                                                                    \
         convert_env(*env, E);                                                                                         \
         convert_ocp(*ocp, O);                                                                                         \
+        count_launches(1);                                                                                            \
         primitives_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                          \
             E, O, B, (const R *)xh, (const R *)u, (const R *)theta, theta_stride, (const R *)target, (R *)x_next,     \
             (R *)A, (R *)Bm, (R *)h, (R *)grad_h, (R *)cost, (R *)u_clamped, active, (R *)b0);                       \
@@ -690,6 +701,7 @@ size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size)
         convert_env(*env, E);                                                                                         \
         convert_ocp(*nom, On);                                                                                        \
         convert_ocp(*aux, Oa);                                                                                        \
+        count_launches(1);                                                                                            \
         plant_step_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                          \
             E, On, Oa, B, (const R *)Un, (const R *)Ua, (const R *)theta_n, sn, (const R *)theta_a, sa,               \
             (const R *)w, (R *)xh, (R *)xhb, (R *)Vn_ws, (R *)Va_ws);                                                 \

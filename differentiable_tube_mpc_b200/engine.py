@@ -48,7 +48,11 @@ class BatchedTubeMPC:
         self.trace = trace
         self.workspace = ops.Workspace(self.device)
         self.timers: Optional[Dict[str, list]] = None   # filled with CUDA events when enabled (bench.py)
-        self.launches = 0                                # kernels of this library launched so far
+
+    @property
+    def launches(self) -> int:
+        """CUDA kernels the library has enqueued in this process so far (counted inside the C-ABI library)."""
+        return ops.kernel_launches()
 
     # -- initial barrier state b0 = B(h(x0) - tight)  (core/barrier.py:111-120) -------------
     def init_barrier(self, x: Tensor, theta: Tensor, nominal: bool) -> Tensor:
@@ -56,7 +60,6 @@ class BatchedTubeMPC:
         B = x.shape[0]
         xh = torch.cat([x, torch.zeros(B, 1, dtype=x.dtype, device=x.device)], dim=1)
         u = torch.zeros(B, 2, dtype=x.dtype, device=x.device)
-        self.launches += 1
         return ops.primitives_batched(self.problem.system, ocp, xh, u, theta)["b0"]
 
     def _timed(self, name):
@@ -87,12 +90,10 @@ class BatchedTubeMPC:
             rn, ra = ops.tube_solve_batched(p.system, p.nominal, p.auxiliary, x0_nom, x0_aux, Vn_init, Va_init,
                                             theta_nom, theta_aux, target=target, gains=self.gains, trace=self.trace,
                                             workspace=self.workspace)
-        self.launches += 1
         with self._timed("sens_aux"):
             sa = ops.ddp_sensitivity_batched(p.system, p.auxiliary, ra.X, ra.V, theta_aux, X_bar=rn.X, X_ref=rn.X,
                                              U_ref=rn.V, want_grads=True, want_ref_grads=full, status=rn.status,
                                              workspace=self.workspace)
-        self.launches += 1
         sn = None
         g_nom_sum = None
         if full:
@@ -103,13 +104,10 @@ class BatchedTubeMPC:
                 sn = ops.ddp_sensitivity_batched(p.system, p.nominal, rn.X, rn.V, theta_nom, upper_grad_x=gx,
                                                  upper_grad_u=sa.g_uref, target=target, want_grads=True,
                                                  status=rn.status, workspace=self.workspace)
-            self.launches += 1
         with self._timed("reduce"):
             g_aux_sum = ops.reduce_columns(torch.cat([sa.g_theta, sa.loss.view(-1, 1)], dim=1), self.workspace)
-            self.launches += 2
             if full:
                 g_nom_sum = ops.reduce_columns(sn.g_theta, self.workspace)
-                self.launches += 2
         return TubeStep(nominal=rn, auxiliary=ra, sens_aux=sa, sens_nom=sn, loss=sa.loss, g_aux_sum=g_aux_sum,
                         g_nom_sum=g_nom_sum)
 

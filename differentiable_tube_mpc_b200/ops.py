@@ -407,6 +407,11 @@ def plant_step_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec,
     _lib.check(rc, "dtmpc_plant_step")
 
 
+def kernel_launches() -> int:
+    """Number of CUDA kernels libdtmpc_b200 has enqueued in this process (dtmpc_kernel_launches)."""
+    return int(_lib.load().dtmpc_kernel_launches())
+
+
 def measure_fp64_peak_tflops(iters: int = 20000) -> float:
     return float(_lib.load().dtmpc_measure_fp64_peak_tflops(int(iters), _stream()))
 

@@ -127,6 +127,8 @@ typedef struct dtmpc_sens_io {
 
 int dtmpc_abi_version(void);
 const char *dtmpc_last_error(void);
+/* Number of CUDA kernels this library has enqueued in this process so far (all entry points, all streams). */
+uint64_t dtmpc_kernel_launches(void);
 
 /* Scratch sizes in bytes (elem_size 8 or 4); pure functions of their arguments (no device needed).
  * n_alpha = number of line-search step sizes (the larger of the two OCPs for a tube solve). */

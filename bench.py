@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--dtype", type=str, default="f64", choices=["f64", "f32"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--warmup-seconds", type=float, default=2.0, help="minimum warm-up wall time (clock ramp)")
     args = ap.parse_args()
     guard_stdout()
@@ -301,15 +302,27 @@ def main():
     h_g = torch.empty(13 + (12 if full else 0), dtype=dtype).pin_memory()
     d2h = sum(t.numel() * t.element_size() for t in (h_u0, h_ub0, h_loss, h_status, h_g))
 
+    # The step (~950 kernel launches at the default size) is captured once into a CUDA graph and replayed: one launch
+    # per step, no per-launch host cost inside the timed region.  --no-graph launches the kernels one by one.
+    graphed = None if args.no_graph else eng.graphed(d_x0n, d_x0a, d_V0, d_V0, d_th_n, d_th_a, full=full)
+
+    def plain_step():
+        return allreduce_shared(eng.step(d_x0n, d_x0a, d_V0, d_V0, d_th_n, d_th_a, full=full))
+
     def device_step():
-        st = eng.step(d_x0n, d_x0a, d_V0, d_V0, d_th_n, d_th_a, full=full)
-        return allreduce_shared(st)
+        if graphed is None:
+            return plain_step()
+        return allreduce_shared(graphed())
 
     def host_step():
-        x0n, x0a = h_x0n.to(dev, non_blocking=True), h_x0a.to(dev, non_blocking=True)
-        V0n, V0a = h_V0n.to(dev, non_blocking=True), h_V0a.to(dev, non_blocking=True)
-        thn, tha = h_th_n.to(dev, non_blocking=True), h_th_a.to(dev, non_blocking=True)
-        st = allreduce_shared(eng.step(x0n, x0a, V0n, V0a, thn, tha, full=full))
+        if graphed is not None:
+            st = allreduce_shared(graphed(x0_nom=h_x0n, x0_aux=h_x0a, Vn_init=h_V0n, Va_init=h_V0a, theta_nom=h_th_n,
+                                          theta_aux=h_th_a))
+        else:
+            x0n, x0a = h_x0n.to(dev, non_blocking=True), h_x0a.to(dev, non_blocking=True)
+            V0n, V0a = h_V0n.to(dev, non_blocking=True), h_V0a.to(dev, non_blocking=True)
+            thn, tha = h_th_n.to(dev, non_blocking=True), h_th_a.to(dev, non_blocking=True)
+            st = allreduce_shared(eng.step(x0n, x0a, V0n, V0a, thn, tha, full=full))
         h_u0.copy_(st.auxiliary.V[:, 0], non_blocking=True)
         h_ub0.copy_(st.nominal.V[:, 0], non_blocking=True)
         h_loss.copy_(st.loss, non_blocking=True)
@@ -345,14 +358,20 @@ def main():
         device_step()
         torch.cuda.synchronize()
         n_warm += 1
+    # per-kernel-group durations (CUDA events around each library call, on the launching stream) and the number of
+    # kernels one step launches: measured on the plain launch path, which is what the graph replays
+    eng.timers = {}
+    l0 = eng.launches
+    for _ in range(max(3, min(args.steps, 10))):
+        plain_step()
+    torch.cuda.synchronize()
+    timers, eng.timers = eng.timers, None
+    launches_per_step = (eng.launches - l0) // max(3, min(args.steps, 10))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    eng.timers = {}
-    l0 = eng.launches
     ms_total, last = timed(device_step, args.steps)
-    launches = eng.launches - l0
-    timers, eng.timers = eng.timers, None
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         host_step()
@@ -397,7 +416,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                "gpu_launches": launches, "launch_mode": "plain" if graphed is None else "cuda_graph_replay",
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "nonfinite_instances": n_bad}
         emit(line)
     if world > 1:

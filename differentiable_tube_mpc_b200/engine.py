@@ -54,6 +54,11 @@ class BatchedTubeMPC:
         """CUDA kernels the library has enqueued in this process so far (counted inside the C-ABI library)."""
         return ops.kernel_launches()
 
+    def graphed(self, x0_nom: Tensor, x0_aux: Tensor, Vn_init: Tensor, Va_init: Tensor, theta_nom: Tensor,
+                theta_aux: Tensor, full: Optional[bool] = None) -> "GraphedStep":
+        """step() captured into a CUDA graph for these shapes (see GraphedStep)."""
+        return GraphedStep(self, x0_nom, x0_aux, Vn_init, Va_init, theta_nom, theta_aux, full=full)
+
     # -- initial barrier state b0 = B(h(x0) - tight)  (core/barrier.py:111-120) -------------
     def init_barrier(self, x: Tensor, theta: Tensor, nominal: bool) -> Tensor:
         ocp = self.problem.nominal if nominal else self.problem.auxiliary
@@ -110,6 +115,41 @@ class BatchedTubeMPC:
                 g_nom_sum = ops.reduce_columns(sn.g_theta, self.workspace)
         return TubeStep(nominal=rn, auxiliary=ra, sens_aux=sa, sens_nom=sn, loss=sa.loss, g_aux_sum=g_aux_sum,
                         g_nom_sum=g_nom_sum)
+
+
+class GraphedStep:
+    """`BatchedTubeMPC.step` on fixed-shape inputs captured once into a CUDA graph and replayed with one launch.
+
+    A step is ~190 kernel launches per chunk of the batch; replaying them as a graph removes the per-launch host cost
+    and makes the step time independent of host jitter.  Inputs are copied into the graph's static tensors
+    (`graphed(x0_nom=..., ...)`, any subset), results are the static tensors of `self.out`, overwritten by each replay.
+    The library's internal chunk streams fork from and join the capturing stream, so they are part of the graph.
+    """
+
+    NAMES = ("x0_nom", "x0_aux", "Vn_init", "Va_init", "theta_nom", "theta_aux")
+
+    def __init__(self, eng: "BatchedTubeMPC", x0_nom, x0_aux, Vn_init, Va_init, theta_nom, theta_aux, full=None):
+        self.static = {k: v.clone() for k, v in zip(self.NAMES, (x0_nom, x0_aux, Vn_init, Va_init, theta_nom, theta_aux))}
+        args = [self.static[k] for k in self.NAMES]
+        saved, eng.timers = eng.timers, None
+        try:
+            side = torch.cuda.Stream(device=eng.device)
+            side.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(side):   # warm-up: workspaces, library streams and allocator pools exist before capture
+                for _ in range(2):
+                    eng.step(*args, full=full)
+            torch.cuda.current_stream(eng.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = eng.step(*args, full=full)
+        finally:
+            eng.timers = saved
+
+    def __call__(self, **inputs) -> TubeStep:
+        for k, v in inputs.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 def allreduce_shared(step: TubeStep, group=None) -> TubeStep:

@@ -76,6 +76,22 @@ class Workspace:
         return b
 
 
+_const_cache: Dict[tuple, Tensor] = {}
+
+
+def _const_tensor(values, dtype, device) -> Tensor:
+    """Small host constant (the fixed target) as a device tensor, uploaded once per (values, dtype, device): a
+    pageable host-to-device copy per call would serialise the stream and cannot be captured into a CUDA graph."""
+    device = torch.device(device)
+    key = (tuple(float(v) for v in values), dtype, device.type, device.index if device.index is not None
+           else torch.cuda.current_device())
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.tensor(list(key[0]), dtype=dtype, device=device)
+        _const_cache[key] = t
+    return t
+
+
 _default_ws: Dict[int, Workspace] = {}
 
 
@@ -141,7 +157,7 @@ def ilqr_solve_batched(system: SystemSpec, ocp: OcpSpec, x0: Tensor, V_init: Ten
         U_ref = _chk(U_ref, (B, T, 2), dtype, "U_ref")
     else:
         if target is None:
-            target = torch.tensor(system.y_target, dtype=dtype, device=device)
+            target = _const_tensor(system.y_target, dtype, device)
         target, gs = _target_arg(target, B, dtype)
     out = _alloc_solve(B, T, ocp.ilqr.max_iter, dtype, device, gains, trace)
     io = _lib.SolveIO()
@@ -174,7 +190,7 @@ def tube_solve_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec,
     theta_nom, tsn = _theta_arg(theta_nom, B, dtype)
     theta_aux, tsa = _theta_arg(theta_aux, B, dtype)
     if target is None:
-        target = torch.tensor(system.y_target, dtype=dtype, device=device)
+        target = _const_tensor(system.y_target, dtype, device)
     target, gs = _target_arg(target, B, dtype)
     on = _alloc_solve(B, T, nominal.ilqr.max_iter, dtype, device, gains, trace)
     oa = _alloc_solve(B, T, auxiliary.ilqr.max_iter, dtype, device, gains, trace, status=on["status"])
@@ -242,7 +258,7 @@ def ddp_sensitivity_batched(system: SystemSpec, ocp: OcpSpec, X: Tensor, V: Tens
         io.Xref, io.Uref, io.xref_row = _ptr(X_ref), _ptr(U_ref), row
     else:
         if target is None:
-            target = torch.tensor(system.y_target, dtype=dtype, device=device)
+            target = _const_tensor(system.y_target, dtype, device)
         target, gs = _target_arg(target, B, dtype)
         io.target, io.target_stride = _ptr(target), gs
     keep += [upper_grad_x, upper_grad_u, X_bar, X_ref, U_ref, target]
@@ -297,7 +313,7 @@ def ift_accumulate_batched(system: SystemSpec, ocp: OcpSpec, X: Tensor, V: Tenso
         io.Xref, io.Uref, io.xref_row = _ptr(X_ref), _ptr(U_ref), row
     else:
         if target is None:
-            target = torch.tensor(system.y_target, dtype=dtype, device=device)
+            target = _const_tensor(system.y_target, dtype, device)
         target, gs = _target_arg(target, B, dtype)
         io.target, io.target_stride = _ptr(target), gs
     res = SensitivityResult(delta_X=dX, delta_V=dV, delta_lambda=dL,
@@ -365,7 +381,7 @@ def primitives_batched(system: SystemSpec, ocp: OcpSpec, xh: Tensor, u: Tensor, 
     u = _chk(u, (B, 2), dtype, "u")
     theta, ts = _theta_arg(theta, B, dtype)
     if target is None:
-        target = torch.tensor(system.y_target, dtype=dtype, device=device)
+        target = _const_tensor(system.y_target, dtype, device)
     target = _chk(target, (3,), dtype, "target")
     e = lambda *s: torch.empty(*s, dtype=dtype, device=device)
     out = dict(x_next=e(B, 4), A=e(B, 4, 4), B=e(B, 4, 2), h=e(B), grad_h=e(B, 3), cost=e(B), u_clamped=e(B, 2),

@@ -85,7 +85,8 @@ typedef struct dtmpc_ocp {
     int32_t reserved;
 } dtmpc_ocp;
 
-/* Buffers of one batched iLQR solve.  Optional pointers may be NULL. */
+/* Buffers of one batched iLQR solve.  Optional pointers may be NULL.  X, V, K, kff must be 16-byte aligned (they are
+ * written with vector stores; cudaMalloc and torch allocations are). */
 typedef struct dtmpc_solve_io {
     const void *x0;                 /* real [B,4]   augmented initial state (x, y, heading, b)       */
     const void *V_init;             /* real [B,T,2] warm start                                       */

@@ -267,7 +267,7 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     from differentiable_tube_mpc_b200 import _lib, ops
-    from differentiable_tube_mpc_b200.engine import BatchedTubeMPC, allreduce_shared, shard_bounds
+    from differentiable_tube_mpc_b200.engine import BatchedTubeMPC, DoubleBufferedSteps, allreduce_shared, shard_bounds
 
     _lib.load()
     torch.cuda.set_device(local_rank)
@@ -314,21 +314,34 @@ def main():
             return plain_step()
         return allreduce_shared(graphed())
 
-    def host_step():
-        if graphed is not None:
-            st = allreduce_shared(graphed(x0_nom=h_x0n, x0_aux=h_x0a, Vn_init=h_V0n, Va_init=h_V0a, theta_nom=h_th_n,
-                                          theta_aux=h_th_a))
-        else:
-            x0n, x0a = h_x0n.to(dev, non_blocking=True), h_x0a.to(dev, non_blocking=True)
-            V0n, V0a = h_V0n.to(dev, non_blocking=True), h_V0a.to(dev, non_blocking=True)
-            thn, tha = h_th_n.to(dev, non_blocking=True), h_th_a.to(dev, non_blocking=True)
-            st = allreduce_shared(eng.step(x0n, x0a, V0n, V0a, thn, tha, full=full))
+    # end to end: every step copies its inputs from pinned host memory and reads its results back.  Two graphed steps
+    # with separate static inputs alternate, so the copy of step i+1 (copy stream) overlaps the kernels of step i.
+    h_inputs = dict(x0_nom=h_x0n, x0_aux=h_x0a, Vn_init=h_V0n, Va_init=h_V0a, theta_nom=h_th_n, theta_aux=h_th_a)
+    dbuf = None if args.no_graph else DoubleBufferedSteps(eng, d_x0n, d_x0a, d_V0, d_V0, d_th_n, d_th_a, full=full)
+
+    def read_back(st):
         h_u0.copy_(st.auxiliary.V[:, 0], non_blocking=True)
         h_ub0.copy_(st.nominal.V[:, 0], non_blocking=True)
         h_loss.copy_(st.loss, non_blocking=True)
         h_status.copy_(st.status, non_blocking=True)
         h_g.copy_(torch.cat([st.g_aux_sum] + ([st.g_nom_sum] if full else [])), non_blocking=True)
-        return st
+
+    def host_steps(n):
+        last = None
+        if dbuf is None:
+            for _ in range(n):
+                dv = {k: v.to(dev, non_blocking=True) for k, v in h_inputs.items()}
+                last = allreduce_shared(eng.step(dv["x0_nom"], dv["x0_aux"], dv["Vn_init"], dv["Va_init"],
+                                                 dv["theta_nom"], dv["theta_aux"], full=full))
+                read_back(last)
+            return last
+        dbuf.prefetch(**h_inputs)
+        for i in range(n):
+            if i + 1 < n:
+                dbuf.prefetch(**h_inputs)
+            last = allreduce_shared(dbuf.run())
+            read_back(last)
+        return last
 
     def barrier():
         if world > 1:
@@ -340,8 +353,11 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
-        for _ in range(steps):
-            last = fn()
+        if fn is host_steps:
+            last = fn(steps)
+        else:
+            for _ in range(steps):
+                last = fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -373,9 +389,8 @@ def main():
     ms_total, last = timed(device_step, args.steps)
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        host_step()
-    ms_e2e, last_h = timed(host_step, args.steps)
+    host_steps(2)
+    ms_e2e, last_h = timed(host_steps, args.steps)
     torch.cuda.synchronize()
 
     n_bad = int((last.status != 0).sum())

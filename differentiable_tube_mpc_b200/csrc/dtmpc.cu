@@ -198,7 +198,7 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
 // another.  Results do not depend on the chunking (every instance is computed by the same instruction sequence).
 // ---------------------------------------------------------------------------
 #ifndef DTMPC_DEFAULT_CHUNKS
-#define DTMPC_DEFAULT_CHUNKS 2
+#define DTMPC_DEFAULT_CHUNKS 4
 #endif
 constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_DEVICES = 64;

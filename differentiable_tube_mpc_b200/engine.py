@@ -152,6 +152,50 @@ class GraphedStep:
         return self.out
 
 
+class DoubleBufferedSteps:
+    """Two graphed steps with separate static inputs, used alternately: `prefetch(**host_inputs)` copies the NEXT
+    step's inputs from (pinned) host memory on a copy stream while the current step's kernels run; `run()` waits for
+    its inputs, replays the graph and returns the static results of that buffer (valid until the second next run).
+
+        db = DoubleBufferedSteps(eng, x0_nom, x0_aux, Vn, Va, th_n, th_a)
+        db.prefetch(**inputs[0])
+        for i in range(n):
+            if i + 1 < n: db.prefetch(**inputs[i + 1])
+            out = db.run()
+    """
+
+    def __init__(self, eng: "BatchedTubeMPC", *args, full=None):
+        self.steps = [GraphedStep(eng, *args, full=full) for _ in range(2)]
+        self.device = eng.device
+        self.copy_stream = torch.cuda.Stream(device=eng.device)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.done = [None, None]
+        self.n_prefetched = 0
+        self.n_run = 0
+
+    def prefetch(self, **host_inputs) -> None:
+        slot = self.n_prefetched % 2
+        assert self.n_prefetched - self.n_run < 2, "at most two steps in flight"
+        with torch.cuda.stream(self.copy_stream):
+            if self.done[slot] is not None:            # the graph that last read these static inputs has finished
+                self.copy_stream.wait_event(self.done[slot])
+            for k, v in host_inputs.items():
+                self.steps[slot].static[k].copy_(v, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.n_prefetched += 1
+
+    def run(self) -> TubeStep:
+        slot = self.n_run % 2
+        assert self.n_prefetched > self.n_run, "run() without a prefetch()"
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[slot])
+        out = self.steps[slot]()
+        self.done[slot] = torch.cuda.Event()
+        self.done[slot].record(cur)
+        self.n_run += 1
+        return out
+
+
 def allreduce_shared(step: TubeStep, group=None) -> TubeStep:
     """Sum the batch-summed gradients (and the loss) over the data-parallel ranks: the one collective of the path
     (Algorithm 2 with shared theta; < 200 bytes, latency bound).  No-op without an initialised process group."""

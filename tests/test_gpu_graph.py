@@ -102,3 +102,32 @@ np.savez(sys.argv[1], nX=st.nominal.X.cpu().numpy(), aX=st.auxiliary.X.cpu().num
     for o in outs[1:]:
         for k in outs[0].files:
             assert np.array_equal(outs[0][k], o[k]), k
+
+
+def test_double_buffered_steps_overlap_copies_without_changing_results():
+    from differentiable_tube_mpc_b200.engine import DoubleBufferedSteps
+
+    B, T = 4096, 10
+    eng, args = _problem(B, T, "paper")
+    names = ("x0_nom", "x0_aux", "Vn_init", "Va_init", "theta_nom", "theta_aux")
+    variants = []
+    for s in range(4):       # four different steps' inputs in pinned host memory
+        a = [t.clone() for t in args]
+        a[1][:, 0] += 0.01 * s
+        a[1][:, 1] -= 0.02 * s
+        variants.append(a)
+    host = [{k: v.cpu().pin_memory() for k, v in zip(names, a)} for a in variants]
+    want = [eng.step(*a, full=False) for a in variants]
+    want = [(w.auxiliary.X.clone(), w.loss.clone(), w.g_aux_sum.clone()) for w in want]
+    db = DoubleBufferedSteps(eng, *args, full=False)
+    db.prefetch(**host[0])
+    for i in range(4):
+        if i + 1 < 4:
+            db.prefetch(**host[i + 1])
+        out = db.run()
+        got = (out.auxiliary.X.clone(), out.loss.clone(), out.g_aux_sum.clone())
+        torch.cuda.synchronize()
+        for g, w in zip(got, want[i]):
+            assert torch.equal(g, w), i
+    with pytest.raises(AssertionError):
+        db.run()

@@ -387,6 +387,28 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 #ifndef DTMPC_FWD_MAXNREG
 #define DTMPC_FWD_MAXNREG 96
 #endif
+// The per-instance parameters a rollout step needs (12 values) are the same for every candidate warp of the CTA and
+// constant over the sweep: parked in shared memory and re-read each step they cost 12 LDS instead of ~24 registers.
+#ifndef DTMPC_FWD_SMEM_THETA
+#define DTMPC_FWD_SMEM_THETA 1
+#endif
+constexpr int TH_ROWS = 14;
+template <typename R> __device__ __forceinline__ void theta_park(R *s, int lane, const Theta<R> &t) {
+    R *v = s + lane;
+    v[0 * 32] = t.Q0; v[1 * 32] = t.Q1; v[2 * 32] = t.Q2; v[3 * 32] = t.R0; v[4 * 32] = t.R1; v[5 * 32] = t.qb;
+    v[6 * 32] = t.gamma; v[7 * 32] = t.tight; v[8 * 32] = t.a_dyn; v[9 * 32] = t.c1_dyn; v[10 * 32] = t.c2_dyn;
+    v[11 * 32] = t.c3_dyn; v[12 * 32] = t.a_jac; v[13 * 32] = t.jac_off;
+}
+template <typename R> __device__ __forceinline__ void theta_fetch(const R *s, int lane, Theta<R> &t) {
+    const volatile R *v = s + lane;  // volatile: re-read every step, never hoisted back into registers
+    t.Q0 = v[0 * 32]; t.Q1 = v[1 * 32]; t.Q2 = v[2 * 32]; t.R0 = v[3 * 32]; t.R1 = v[4 * 32]; t.qb = v[5 * 32];
+    t.gamma = v[6 * 32]; t.tight = v[7 * 32]; t.a_dyn = v[8 * 32]; t.c1_dyn = v[9 * 32]; t.c2_dyn = v[10 * 32];
+    t.c3_dyn = v[11 * 32];
+}
+template <typename R> __device__ __forceinline__ void theta_fetch_jac(const R *s, int lane, Theta<R> &t) {
+    const volatile R *v = s + lane;
+    t.a_jac = v[12 * 32]; t.jac_off = v[13 * 32];
+}
 constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 
 template <typename R, int NC, int NOBS = -1>
@@ -423,6 +445,12 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
     const R *ref_i = P.ws.ref + tile_off(i, ref_rows(T));
     R *CK = P.ws.ckpt + tile_off(j, (long long)CR * (MAX_SEG - 1) * P.n_eval);
 
+#if DTMPC_FWD_SMEM_THETA
+    __shared__ R sTh[TH_ROWS * 32];
+    if (threadIdx.y == 0) theta_park(sTh, lane, th);
+    __syncthreads();
+#endif
+
     State<R> x[NC];
     R J[NC];
     {
@@ -458,6 +486,13 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         xp += TR * 32;  // one running pointer per stream: every load is pointer + immediate
         gp += GR * 32;
         rp += RR * 32;
+#if DTMPC_FWD_SMEM_THETA
+        Theta<R> tk;
+        tk.eps_dyn = P.ocp.eps_dyn; tk.angle_wrap = P.ocp.angle_wrap;
+        theta_fetch(sTh, lane, tk);
+#else
+        const Theta<R> &tk = th;
+#endif
         R u0[NC], u1[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
@@ -468,9 +503,9 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
             u0[q] = m::fma_(al[q], du0, v0);
             u1[q] = m::fma_(al[q], du1, v1);
             clamp_u(E, u0[q], u1[q]);
-            J[q] += stage_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, u0[q], u1[q], r.x0, r.x1, r.x2, r.u0, r.u1);
+            J[q] += stage_cost(tk, x[q].px, x[q].py, x[q].th, x[q].b, u0[q], u1[q], r.x0, r.x1, r.x2, r.u0, r.u1);
         }
-        step_multi<R, NC, NOBS>(E, th, x, u0, u1);
+        step_multi<R, NC, NOBS>(E, tk, x, u0, u1);
     }
     RefPt<R> r;
     ref_at(P, rp, false, t0, t1, t2, r);
@@ -536,6 +571,9 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
 #ifndef DTMPC_SEL_MAXNREG
 #define DTMPC_SEL_MAXNREG 96
 #endif
+#ifndef DTMPC_SEL_SMEM_THETA
+#define DTMPC_SEL_SMEM_THETA 0  // measured neutral for the commit sweep (18.22 vs 18.21 ms)
+#endif
 __device__ __forceinline__ void st4(double *p, double a, double b, double c, double d) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
     reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
@@ -557,13 +595,21 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
     }
     const int lane = threadIdx.x, seg = threadIdx.y;
     const int j = blockIdx.x * 32 + lane;
+    const bool live = j < n_act;
+    const long long i = live ? P.ws.list[P.parity][j] : 0;
+    Theta<R> th;
+    if (live) load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+#if DTMPC_SEL_SMEM_THETA
+    __shared__ R sTh[TH_ROWS * 32];
+    if (live && seg == 0) theta_park(sTh, lane, th);  // visible after the barrier below
+#endif
     // rank of this CTA's first slot among the running instances
     int acc = 0;
     for (int w = seg * 32 + lane; w < (int)blockIdx.x; w += 32 * blockDim.y) acc += __popc(P.ws.keep[w]);
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) s_part[seg] = acc;
     __syncthreads();
-    if (j >= n_act) return;
+    if (!live) return;
     int base = 0;
     for (int q = 0; q < (int)blockDim.y; ++q) base += s_part[q];
     const unsigned mine = P.ws.keep[blockIdx.x];
@@ -571,7 +617,6 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
 
     const int d = P.ws.dec[j];
     const bool keep = (d & DEC_KEEP) != 0;
-    const long long i = P.ws.list[P.parity][j];
     const long long jn = base + __popc(mine & ((1u << lane) - 1u));
     if (keep && seg == 0) P.ws.list[P.parity ^ 1][jn] = (int)i;
     const R al = (d & DEC_BAD) ? R(0) : P.ocp.alphas[d & 0xff];
@@ -580,8 +625,6 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
     const EnvT<R> &E = P.env;
     const int T = P.ocp.T;
     const int k_lo = seg * P.seg_len, k_hi = min(T, k_lo + P.seg_len);
-    Theta<R> th;
-    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
     const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
     const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
     // destinations: next slot (running) or the result tensors (stopping)
@@ -621,13 +664,21 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
         const R N2 = xp[(TR + 2) * 32], N3 = xp[(TR + 3) * 32];
         R u0 = v0, u1 = v1, gx, gy;
         if (!copy) {
+#if DTMPC_SEL_SMEM_THETA
+            Theta<R> tk;
+            tk.eps_dyn = P.ocp.eps_dyn; tk.eps_jac = P.ocp.eps_jac; tk.angle_wrap = P.ocp.angle_wrap;
+            theta_fetch(sTh, lane, tk);
+            theta_fetch_jac(sTh, lane, tk);
+#else
+            const Theta<R> &tk = th;
+#endif
             const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
             const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
             const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
             u0 = m::fma_(al, du0, v0);
             u1 = m::fma_(al, du1, v1);
             clamp_u(E, u0, u1);
-            step_g<R, NOBS>(E, th, x, u0, u1, gx, gy);
+            step_g<R, NOBS>(E, tk, x, u0, u1, gx, gy);
         } else {
             x.px = N0; x.py = N1; x.th = N2; x.b = N3;
             gx = xp[(TR + 6) * 32];

@@ -112,6 +112,32 @@ template <typename R> __device__ __forceinline__ void cp_async_elem(R *smem_dst,
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(sizeof(R)) : "memory");
 }
+// Bulk asynchronous copy (the TMA engine without a tensor map): one thread moves a contiguous block global -> shared
+// and the bytes are accounted on an mbarrier; consumers wait on the barrier's phase.  PTX ISA 8.x, sm_90+.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+    while (!mbar_try_wait(b, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -392,6 +418,19 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 #ifndef DTMPC_FWD_SMEM_THETA
 #define DTMPC_FWD_SMEM_THETA 1
 #endif
+// Inputs of a line-search step (x_k, u_k: 6 rows; K_k, k_k: 10 rows of the CTA's tile) staged through a ring of
+// shared-memory buffers by bulk asynchronous copies issued DTMPC_FWD_STAGES steps ahead by one thread; every candidate
+// warp reads them from shared memory.  0: each warp loads them itself (L1 serves the repeats).
+// Measured (B = 65,536, T = 50, same box): staged 14.55 / 18.36 ms, plain loads 14.27 / 18.23 ms per tube solve
+// (paper / full mode; 3, 4 and 6 stages alike): the L1 already serves three of four warps and the per-step barrier
+// traffic costs more than the exposed latency it removes, so the plain path stays the default.
+#ifndef DTMPC_FWD_TMA
+#define DTMPC_FWD_TMA 0
+#endif
+#ifndef DTMPC_FWD_STAGES
+#define DTMPC_FWD_STAGES 4
+#endif
+constexpr int XR = 6;
 constexpr int TH_ROWS = 14;
 template <typename R> __device__ __forceinline__ void theta_park(R *s, int lane, const Theta<R> &t) {
     R *v = s + lane;
@@ -463,6 +502,31 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
     }
     int k_ck = P.seg_len, seg = 0;  // next segment boundary
     const R *xp = X, *gp = GK, *rp = ref_i;
+#if DTMPC_FWD_TMA
+    constexpr int ST = DTMPC_FWD_STAGES;
+    constexpr unsigned X_BYTES = XR * 32 * sizeof(R), G_BYTES = GR * 32 * sizeof(R);
+    __shared__ __align__(128) R sIn[ST][(XR + GR) * 32];
+    __shared__ __align__(8) unsigned long long sFull[ST], sEmpty[ST];
+    const bool producer = threadIdx.x == 0 && threadIdx.y == 0;
+    const R *tX = P.ws.traj[P.parity] + (long long)blockIdx.x * traj_rows(T) * 32;   // this CTA's tile
+    const R *tG = P.ws.gains + (long long)blockIdx.x * gain_rows(T) * 32;
+    auto issue = [&](int kk) {
+        const int s = kk % ST;
+        mbar_expect_tx(&sFull[s], X_BYTES + G_BYTES);
+        bulk_g2s(&sIn[s][0], tX + (long long)kk * TR * 32, X_BYTES, &sFull[s]);
+        bulk_g2s(&sIn[s][XR * 32], tG + (long long)kk * GR * 32, G_BYTES, &sFull[s]);
+    };
+    if (producer) {
+        for (int s = 0; s < ST; ++s) {
+            mbar_init(&sFull[s], 1);
+            mbar_init(&sEmpty[s], blockDim.y);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (producer)
+        for (int kk = 0; kk < ST && kk < T; ++kk) issue(kk);
+#endif
     for (int k = 0; k < T; ++k) {
         if (k == k_ck) {  // the commit sweep restarts the winner from here (uniform branch)
             if (live) {
@@ -476,11 +540,28 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
             k_ck += P.seg_len;
             ++seg;
         }
+#if DTMPC_FWD_TMA
+        const int st = k % ST;
+        mbar_wait(&sFull[st], (unsigned)(k / ST) & 1u);
+        const R *q = &sIn[st][lane];
+        const R X0 = q[0 * 32], X1 = q[1 * 32], X2 = q[2 * 32], X3 = q[3 * 32];
+        const R v0 = q[4 * 32], v1 = q[5 * 32];
+        const R K00 = q[6 * 32], K01 = q[7 * 32], K02 = q[8 * 32], K03 = q[9 * 32];
+        const R K10 = q[10 * 32], K11 = q[11 * 32], K12 = q[12 * 32], K13 = q[13 * 32];
+        const R k0 = q[14 * 32], k1 = q[15 * 32];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sEmpty[st]);   // this warp is done with the buffer
+        if (producer && k >= 1 && k - 1 + ST < T) {   // refill the buffer every warp released one step ago
+            mbar_wait(&sEmpty[(k - 1) % ST], (unsigned)((k - 1) / ST) & 1u);
+            issue(k - 1 + ST);
+        }
+#else
         const R X0 = xp[0 * 32], X1 = xp[1 * 32], X2 = xp[2 * 32], X3 = xp[3 * 32];
         const R v0 = xp[4 * 32], v1 = xp[5 * 32];
         const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
         const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
         const R k0 = gp[8 * 32], k1 = gp[9 * 32];
+#endif
         RefPt<R> r;
         ref_at(P, rp, true, t0, t1, t2, r);
         xp += TR * 32;  // one running pointer per stream: every load is pointer + immediate

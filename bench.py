@@ -82,7 +82,7 @@ def algorithmic_bytes_per_solve(T, full):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: in-process NVML every 50 ms (an `nvidia-smi -lms`
+    """SM clock and throttle reasons sampled DURING the timed region: in-process NVML every 20 ms (an `nvidia-smi -lms`
     subprocess perturbed the measured step time by ~30 %); falls back to nvidia-smi if NVML is unavailable."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
@@ -121,7 +121,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def stop(self):
         if self.h is None:
@@ -375,14 +375,19 @@ def main():
         torch.cuda.synchronize()
         n_warm += 1
     # per-kernel-group durations (CUDA events around each library call, on the launching stream) and the number of
-    # kernels one step launches: measured on the plain launch path, which is what the graph replays
-    eng.timers = {}
-    l0 = eng.launches
-    for _ in range(max(3, min(args.steps, 10))):
+    # kernels one step launches: measured on the plain launch path, which is what the graph replays.  The plain path
+    # pays ~190 host launches per chunk, so its first steps and any host hiccup inflate a section: median of 9.
+    for _ in range(3):
         plain_step()
     torch.cuda.synchronize()
+    eng.timers = {}
+    l0 = eng.launches
+    n_plain = 9
+    for _ in range(n_plain):
+        plain_step()
+        torch.cuda.synchronize()
     timers, eng.timers = eng.timers, None
-    launches_per_step = (eng.launches - l0) // max(3, min(args.steps, 10))
+    launches_per_step = (eng.launches - l0) // n_plain
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -395,7 +400,7 @@ def main():
 
     n_bad = int((last.status != 0).sum())
     iters_total = int(last.nominal.iters.sum()) + int(last.auxiliary.iters.sum())
-    kern_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
+    kern_ms = {k: float(np.median([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
     value = total * args.steps / (ms_total * 1e-3)
     e2e_val = total * args.steps / (ms_e2e * 1e-3)
 

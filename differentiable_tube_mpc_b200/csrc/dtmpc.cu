@@ -624,7 +624,7 @@ size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_
 uint64_t dtmpc_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size) {
     if (T < 1 || B < 0) return 0;
-    return (size_t)sens_ws_rows(T) * (size_t)B * (size_t)elem_size + 256;
+    return (size_t)sens_ws_rows(T) * (size_t)((B + 31) / 32 * 32) * (size_t)elem_size + 256;  // whole tiles
 }
 size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size) {
     const long long nb = B > 0 ? (B + RED_ROWS - 1) / RED_ROWS : 0;

@@ -3,8 +3,9 @@
 //
 // One problem per thread, static mapping (every instance does exactly one backward and one forward sweep
 // of T steps, so there is no divergence to hide).  The backward sweep stores, per time step, what the
-// forward sweep needs (gains, value blocks, linearisation, h) in an instance-minor SoA scratch
-// ws[row*B + i]: coalesced both ways.
+// forward sweep needs (gains, value blocks, linearisation, h) in a tile-major scratch: 32 consecutive instances form a
+// tile whose rows are contiguous, ws[((i/32)*rows + row)*32 + i%32] -- a warp access is one 256 B segment and every
+// address is the thread's base pointer plus an immediate (a batch-sized row stride costs 64-bit multiplies per access).
 #pragma once
 #include "dtmpc_math.cuh"
 
@@ -74,9 +75,8 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     const EnvT<R> &E = P.env;
     const SensArgs<R> &a = P.io;
     const int T = P.ocp.T;
-    const long long S = P.B;
-    R *const ws = P.ws + i;
-#define WS(row) ws[(long long)(row) * S]
+    R *const ws = P.ws + (i >> 5) * (sens_ws_rows(T) * 32) + (i & 31);
+#define WS(row) ws[(row) * 32]
 #define ROW(k, r) ((k) * SENS_ROWS + (r))
     Theta<R> th;
     load_theta(th, a.theta + i * a.theta_stride, P.ocp);

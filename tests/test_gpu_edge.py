@@ -1,0 +1,103 @@
+"""GPU parity on the shapes the slot/tile/segment machinery could get wrong: horizons shorter than the number of commit
+segments, batches that are not whole tiles of 32, a single instance, step-size lists with one entry or with only
+alpha = 0, an obstacle count without a compile-time instantiation, no obstacles.  Checked against the CPU oracle."""
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_instances, per_instance_rel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+
+
+def _setup(oracle, T, B, seed, n_obs=None, alphas=None, max_iter=None):
+    from differentiable_tube_mpc_b200 import TubeProblem, default_dubins_config
+
+    cfg = default_dubins_config()
+    cfg["system"]["horizon_N"] = int(T)
+    if n_obs is not None:
+        cfg["environment"]["obstacles"] = cfg["environment"]["obstacles"][:n_obs]
+    if alphas is not None:
+        cfg["system"]["line_search_alphas"] = list(alphas)
+    if max_iter is not None:
+        cfg["system"]["nominal_max_iter"] = cfg["system"]["aux_max_iter"] = int(max_iter)
+    prob = TubeProblem.from_config(cfg, mode="paper")
+    env = oracle.env_from_cfg(cfg)
+    nom, aux = oracle.ocps_from_cfg(cfg, "paper")
+    ref_cfg = default_dubins_config()          # start states are drawn against the full obstacle field
+    x, xb = make_instances(B, seed, ref_cfg)
+    b0n = np.array([oracle.b0(env, nom, v) for v in xb])
+    b0a = np.array([oracle.b0(env, aux, v) for v in x])
+    x0n = np.concatenate([xb, b0n[:, None]], axis=1)
+    x0a = np.concatenate([x, b0a[:, None]], axis=1)
+    return prob, env, nom, aux, x0n, x0a
+
+
+def _check(oracle, prob, env, nom, aux, x0n, x0a, T):
+    from differentiable_tube_mpc_b200 import ops
+
+    B = x0n.shape[0]
+    V0 = np.zeros((B, T, 2))
+    want = oracle.tube_solve_batch(env, nom, aux, x0n, x0a, V0, V0, mode="paper", n_threads=4)
+    rn, ra = ops.tube_solve_batched(prob.system, prob.nominal, prob.auxiliary, cu(x0n), cu(x0a), cu(V0), cu(V0),
+                                    cu(prob.theta_nom0), cu(prob.theta_aux0), gains=True, trace=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(rn.status.cpu().numpy() != 0, want["status"] != 0)
+    ok = want["status"] == 0
+    same = ok & (want["iters_n"] == rn.iters.cpu().numpy()) & (want["iters_a"] == ra.iters.cpu().numpy())
+    for i in np.nonzero(same)[0]:
+        same[i] &= np.array_equal(want["aidx_n"][i][: want["iters_n"][i]], rn.alpha_idx.cpu().numpy()[i][: want["iters_n"][i]])
+        same[i] &= np.array_equal(want["aidx_a"][i][: want["iters_a"][i]], ra.alpha_idx.cpu().numpy()[i][: want["iters_a"][i]])
+    assert same.sum() >= 0.8 * max(1, ok.sum()), (same.sum(), ok.sum())   # the rest are roundoff ties (App. B Q12)
+    for got, key in ((rn.X, "Xn"), (rn.V, "Un"), (ra.X, "Xa"), (ra.V, "Ua"), (rn.K, "Kn"), (ra.K, "Ka")):
+        e = per_instance_rel(got.cpu().numpy()[same], want[key][same], floor=1e-6)
+        assert e.size == 0 or np.median(e) < 1e-12, (key, np.median(e))
+        assert e.size == 0 or np.quantile(e, 0.9) < 1e-9, (key, np.quantile(e, 0.9))
+    # whatever the decisions: the returned trajectory is the rollout of the returned controls, bit for bit
+    for r, ocp, th in ((rn, prob.nominal, prob.theta_nom0), (ra, prob.auxiliary, prob.theta_aux0)):
+        x0 = cu(x0n if r is rn else x0a)
+        X = ops.rollout_batched(prob.system, ocp, x0, r.V, cu(th))
+        assert torch.equal(X, r.X)
+
+
+@pytest.mark.parametrize("T,B", [(1, 33), (2, 5), (3, 64), (4, 1), (7, 95), (11, 32)])
+def test_short_horizons_and_ragged_batches(oracle, T, B):
+    prob, env, nom, aux, x0n, x0a = _setup(oracle, T, B, seed=100 + T)
+    _check(oracle, prob, env, nom, aux, x0n, x0a, T)
+
+
+@pytest.mark.parametrize("alphas", [(1.0,), (0.0,), (0.3, 0.0), (0.0, 1.0, 0.5)])
+def test_degenerate_step_size_lists(oracle, alphas):
+    prob, env, nom, aux, x0n, x0a = _setup(oracle, 9, 40, seed=7, alphas=alphas, max_iter=4)
+    _check(oracle, prob, env, nom, aux, x0n, x0a, 9)
+
+
+@pytest.mark.parametrize("n_obs", [0, 1, 3])
+def test_obstacle_counts_without_a_specialised_kernel(oracle, n_obs):
+    prob, env, nom, aux, x0n, x0a = _setup(oracle, 12, 48, seed=31 + n_obs, n_obs=n_obs)
+    _check(oracle, prob, env, nom, aux, x0n, x0a, 12)
+
+
+def test_empty_batch_and_bad_arguments():
+    from differentiable_tube_mpc_b200 import TubeProblem, default_dubins_config, ops
+
+    cfg = default_dubins_config()
+    cfg["system"]["horizon_N"] = 5
+    prob = TubeProblem.from_config(cfg, mode="paper")
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=DEV)
+    rn, ra = ops.tube_solve_batched(prob.system, prob.nominal, prob.auxiliary, z(0, 4), z(0, 4), z(0, 5, 2), z(0, 5, 2),
+                                    cu(prob.theta_nom0), cu(prob.theta_aux0))
+    assert rn.X.shape == (0, 6, 4) and ra.V.shape == (0, 5, 2)
+    with pytest.raises((ValueError, TypeError, RuntimeError)):
+        ops.tube_solve_batched(prob.system, prob.nominal, prob.auxiliary, z(3, 4).cpu(), z(3, 4), z(3, 5, 2), z(3, 5, 2),
+                               cu(prob.theta_nom0), cu(prob.theta_aux0))
+    with pytest.raises((ValueError, TypeError, RuntimeError)):
+        ops.tube_solve_batched(prob.system, prob.nominal, prob.auxiliary, z(3, 4), z(3, 4), z(3, 4, 2), z(3, 5, 2),
+                               cu(prob.theta_nom0), cu(prob.theta_aux0))

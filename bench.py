@@ -408,15 +408,16 @@ def main():
         n_alpha = prob.nominal.ilqr.line_search_alphas
         # dominant work item: the iLQR solve = launch sequence init + max_iter x (ric, fwd, commit) for the
         # nominal and the auxiliary OCP; fwd_kernel (line search) is its largest kernel (ncu share in profiles/)
-        flops = algorithmic_flops(T, len(n_alpha), iters_total, 2 * B, 0)
+        # one library call per step (dtmpc_tube_step): both solves and the sensitivity sweeps of every chunk
+        flops = algorithmic_flops(T, len(n_alpha), iters_total, 2 * B, B * (2 if full else 1))
         peak64 = ops.measure_fp64_peak_tflops() if dtype == torch.float64 else ops.measure_fp32_peak_tflops()
-        ach = flops / (kern_ms["tube_solve"] * 1e-3) / 1e12
+        ach = flops / (kern_ms["tube_step"] * 1e-3) / 1e12
         peaks = measured_peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         step_ms = ms_total / args.steps
         bytes_solve = algorithmic_bytes_per_solve(T, full) * (1 if dtype == torch.float64 else 0.5)
         hbm_ach = bytes_solve * B / (step_ms * 1e-3) / 1e9
-        roofline = {"bound": "fp64" if dtype == torch.float64 else "fp32", "kernel": "dtmpc iLQR launch sequence (init + max_iter x [ric, fwd, commit] per OCP; largest: fwd_kernel)",
+        roofline = {"bound": "fp64" if dtype == torch.float64 else "fp32", "kernel": "dtmpc_tube_step launch sequence (per OCP: init + max_iter x [ric, fwd, commit]; then sens; largest: fwd_kernel)",
                     "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64 if peak64 > 0 else None,
                     "peak_source": "DFMA loop measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                     "flop_model": "SURVEY 8d dense reference form x actual iterations; exp=25 log=30 sincos=50 flop-eq",

@@ -72,16 +72,18 @@ class SensIO(C.Structure):
         ("xref_row", C.c_int64), ("gx", C.c_void_p), ("gu", C.c_void_p), ("Xbar", C.c_void_p),
         ("dX", C.c_void_p), ("dV", C.c_void_p), ("dL", C.c_void_p), ("g_theta", C.c_void_p),
         ("gXref", C.c_void_p), ("gUref", C.c_void_p), ("loss", C.c_void_p), ("status", C.c_void_p),
+        ("gx_row", C.c_int64),
     ]
 
 
 # every symbol include/dtmpc.h declares (tests/test_abi.py checks the header against this list)
-_PER_DTYPE = ("ilqr_solve", "tube_solve", "sensitivity", "ift_accumulate", "reduce_columns", "rollout", "primitives",
+_PER_DTYPE = ("ilqr_solve", "tube_solve", "tube_step", "sensitivity", "ift_accumulate", "reduce_columns", "rollout", "primitives",
               "plant_step")
-EXPORTS = ["dtmpc_abi_version", "dtmpc_last_error", "dtmpc_kernel_launches", "dtmpc_solve_workspace_bytes", "dtmpc_sens_workspace_bytes",
+EXPORTS = ["dtmpc_abi_version", "dtmpc_last_error", "dtmpc_kernel_launches", "dtmpc_solve_workspace_bytes", "dtmpc_sens_workspace_bytes", "dtmpc_step_workspace_bytes",
            "dtmpc_reduce_workspace_bytes", "dtmpc_measure_fp64_peak_tflops", "dtmpc_measure_fp32_peak_tflops"] + [
     f"dtmpc_{n}_{s}" for n in _PER_DTYPE for s in ("f64", "f32")]
 
+ABI_VERSION = 2   # include/dtmpc.h DTMPC_ABI_VERSION
 _lib = None
 
 
@@ -106,6 +108,8 @@ def load() -> C.CDLL:
     L.dtmpc_kernel_launches.restype = C.c_uint64
     L.dtmpc_solve_workspace_bytes.restype = sz
     L.dtmpc_solve_workspace_bytes.argtypes = [i32, i64, i32, i32]
+    L.dtmpc_step_workspace_bytes.restype = sz
+    L.dtmpc_step_workspace_bytes.argtypes = [i32, i64, i32, i32]
     L.dtmpc_sens_workspace_bytes.restype = sz
     L.dtmpc_sens_workspace_bytes.argtypes = [i32, i64, i32]
     L.dtmpc_reduce_workspace_bytes.restype = sz
@@ -115,6 +119,9 @@ def load() -> C.CDLL:
         f.restype, f.argtypes = C.c_int, [pe, po, i64, C.POINTER(SolveIO), vp, sz, vp]
         f = getattr(L, f"dtmpc_tube_solve_{s}")
         f.restype, f.argtypes = C.c_int, [pe, po, po, i64, C.POINTER(SolveIO), C.POINTER(SolveIO), vp, sz, vp]
+        f = getattr(L, f"dtmpc_tube_step_{s}")
+        f.restype, f.argtypes = C.c_int, [pe, po, po, i64, C.POINTER(SolveIO), C.POINTER(SolveIO), C.POINTER(SensIO),
+                                          C.POINTER(SensIO), vp, sz, vp]
         f = getattr(L, f"dtmpc_sensitivity_{s}")
         f.restype, f.argtypes = C.c_int, [pe, po, i64, C.POINTER(SensIO), vp, sz, vp]
         f = getattr(L, f"dtmpc_ift_accumulate_{s}")
@@ -131,7 +138,7 @@ def load() -> C.CDLL:
     L.dtmpc_measure_fp64_peak_tflops.argtypes = [i32, vp]
     L.dtmpc_measure_fp32_peak_tflops.restype = C.c_double
     L.dtmpc_measure_fp32_peak_tflops.argtypes = [i32, vp]
-    if L.dtmpc_abi_version() != 1:
+    if L.dtmpc_abi_version() != ABI_VERSION:
         raise RuntimeError("libdtmpc_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -190,6 +190,66 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     return DTMPC_OK;
 }
 
+template <typename R> void convert_sens(const dtmpc_sens_io &s, SensArgs<R> &a) {
+    a.X = (const R *)s.X; a.V = (const R *)s.V; a.theta = (const R *)s.theta; a.target = (const R *)s.target;
+    a.Xref = (const R *)s.Xref; a.Uref = (const R *)s.Uref; a.gx = (const R *)s.gx; a.gu = (const R *)s.gu;
+    a.Xbar = (const R *)s.Xbar;
+    a.theta_stride = s.theta_stride; a.target_stride = s.target_stride; a.xref_row = s.xref_row;
+    a.gx_row = s.gx_row == 0 ? 4 : s.gx_row;
+    a.dX = (R *)s.dX; a.dV = (R *)s.dV; a.dL = (R *)s.dL; a.g_theta = (R *)s.g_theta;
+    a.gXref = (R *)s.gXref; a.gUref = (R *)s.gUref; a.loss = (R *)s.loss; a.status = s.status;
+}
+
+bool sens_io_ok(const dtmpc_sens_io *s, bool accumulate_only) {
+    if (!s || !s->X || !s->V || !s->theta || !s->dX || !s->dV || !s->dL) return false;
+    if ((s->Xref == nullptr) != (s->Uref == nullptr)) return false;
+    if (s->Xref && s->xref_row != 3 && s->xref_row != 4) return false;
+    if (s->gx_row != 0 && s->gx_row != 3 && s->gx_row != 4) return false;
+    const bool wants_cost_ref = s->g_theta || accumulate_only;
+    if (wants_cost_ref && !s->Xref && !s->target) return false;
+    if (!accumulate_only && !s->gx && !s->Xbar) return false;
+    return true;
+}
+
+template <typename R> void offset_sens_io(SensArgs<R> &a, long long off, int T) {
+    a.X += off * 4LL * (T + 1);
+    a.V += off * 2LL * T;
+    a.theta += off * a.theta_stride;
+    if (a.target) a.target += off * a.target_stride;
+    if (a.Xref) a.Xref += off * a.xref_row * (T + 1);
+    if (a.Uref) a.Uref += off * 2LL * T;
+    if (a.gx) a.gx += off * a.gx_row * (T + 1);
+    if (a.gu) a.gu += off * 2LL * T;
+    if (a.Xbar) a.Xbar += off * 4LL * (T + 1);
+    a.dX += off * 4LL * (T + 1);
+    a.dV += off * 2LL * T;
+    a.dL += off * 4LL * (T + 1);
+    if (a.g_theta) a.g_theta += off * DTMPC_NTHETA;
+    if (a.gXref) a.gXref += off * 3LL * (T + 1);
+    if (a.gUref) a.gUref += off * 2LL * T;
+    if (a.loss) a.loss += off;
+    if (a.status) a.status += off;
+}
+
+// sensitivity sweep of instances [off, off + Bc) on stream st, scratch at ws (sens_ws_rows(T) rows of whole tiles)
+template <typename R>
+int launch_sens_chunk(const dtmpc_env *env, const dtmpc_ocp *ocp, const dtmpc_sens_io *io, long long off, long long Bc,
+                      void *ws, cudaStream_t st) {
+    SensParams<R> P;
+    memset(&P, 0, sizeof(P));
+    convert_env(*env, P.env);
+    convert_ocp(*ocp, P.ocp);
+    convert_sens(*io, P.io);
+    offset_sens_io(P.io, off, ocp->horizon);
+    P.B = Bc;
+    P.ws = (R *)ws;
+    sens_kernel<R><<<(unsigned)((Bc + SENS_BLOCK - 1) / SENS_BLOCK), SENS_BLOCK, 0, st>>>(P);
+    count_launches(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "sensitivity kernel launch");
+    return DTMPC_OK;
+}
+
 // ---------------------------------------------------------------------------
 // Chunked execution.  The backward and commit sweeps are serial chains of T steps with one thread per instance: at
 // B = 65,536 they are a single wave of 14 warps per SM whose duration is the latency of one chain however few
@@ -261,7 +321,8 @@ template <typename R> void offset_io(SolveArgs<R> &a, long long off, int T, int 
 
 template <typename R>
 int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, long long B, const dtmpc_solve_io *io0,
-               const dtmpc_solve_io *io1, void *ws, size_t ws_bytes, void *stream) {
+               const dtmpc_solve_io *io1, void *ws, size_t ws_bytes, void *stream, const dtmpc_sens_io *sa = nullptr,
+               const dtmpc_sens_io *sn = nullptr, bool with_sens = false) {
     if (!env_ok(env) || !ocp_ok(o0) || (o1 && !ocp_ok(o1))) return fail(DTMPC_E_BADARG, "bad env/ocp description");
     if (o1 && o1->horizon != o0->horizon) return fail(DTMPC_E_BADARG, "nominal and auxiliary horizons differ");
     if (B < 0 || B > 0x7fffffffLL) return fail(DTMPC_E_BADARG, "batch size out of range");
@@ -275,8 +336,14 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
             if (((uintptr_t)q & 15u) != 0) return fail(DTMPC_E_BADARG, "result buffers must be 16-byte aligned");
     }
     const int n_alpha = o1 && o1->n_alpha > o0->n_alpha ? o1->n_alpha : o0->n_alpha;
-    if (ws_bytes < dtmpc_solve_workspace_bytes(o0->horizon, B, n_alpha, (int)sizeof(R)))
+    if (with_sens) {
+        if (!o1 || !sens_io_ok(sa, false) || (sn && !sens_io_ok(sn, false)))
+            return fail(DTMPC_E_BADARG, "missing buffer in the sensitivity io of a tube step");
+        if (ws_bytes < dtmpc_step_workspace_bytes(o0->horizon, B, n_alpha, (int)sizeof(R)))
+            return fail(DTMPC_E_WORKSPACE, "step workspace too small");
+    } else if (ws_bytes < dtmpc_solve_workspace_bytes(o0->horizon, B, n_alpha, (int)sizeof(R))) {
         return fail(DTMPC_E_WORKSPACE, "solve workspace too small");
+    }
     const cudaStream_t user = (cudaStream_t)stream;
     const int T = o0->horizon;
 
@@ -324,6 +391,13 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
             P.status_shift = 4;
             rc = launch_ocp(P, st);
         }
+        if (rc == DTMPC_OK && with_sens) {
+            // the chunk's sensitivity sweeps follow its solves on the same stream (scratch: after the solver arrays)
+            void *sws = (char *)ws + ws_off;
+            ws_off += align_up((size_t)sens_ws_rows(T) * (size_t)((Bc + 31) / 32 * 32) * sizeof(R));
+            rc = launch_sens_chunk<R>(env, o1, sa, off, Bc, sws, st);
+            if (rc == DTMPC_OK && sn) rc = launch_sens_chunk<R>(env, o0, sn, off, Bc, sws, st);
+        }
         if (c > 0) {  // join, also after a failed launch: the caller's stream must not run ahead of the chunk
             cudaError_t e = cudaEventRecord(cs->done[c], st);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(user, cs->done[c], 0);
@@ -331,25 +405,6 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
         }
     }
     return rc;
-}
-
-template <typename R> void convert_sens(const dtmpc_sens_io &s, SensArgs<R> &a) {
-    a.X = (const R *)s.X; a.V = (const R *)s.V; a.theta = (const R *)s.theta; a.target = (const R *)s.target;
-    a.Xref = (const R *)s.Xref; a.Uref = (const R *)s.Uref; a.gx = (const R *)s.gx; a.gu = (const R *)s.gu;
-    a.Xbar = (const R *)s.Xbar;
-    a.theta_stride = s.theta_stride; a.target_stride = s.target_stride; a.xref_row = s.xref_row;
-    a.dX = (R *)s.dX; a.dV = (R *)s.dV; a.dL = (R *)s.dL; a.g_theta = (R *)s.g_theta;
-    a.gXref = (R *)s.gXref; a.gUref = (R *)s.gUref; a.loss = (R *)s.loss; a.status = s.status;
-}
-
-bool sens_io_ok(const dtmpc_sens_io *s, bool accumulate_only) {
-    if (!s || !s->X || !s->V || !s->theta || !s->dX || !s->dV || !s->dL) return false;
-    if ((s->Xref == nullptr) != (s->Uref == nullptr)) return false;
-    if (s->Xref && s->xref_row != 3 && s->xref_row != 4) return false;
-    const bool wants_cost_ref = s->g_theta || accumulate_only;
-    if (wants_cost_ref && !s->Xref && !s->target) return false;
-    if (!accumulate_only && !s->gx && !s->Xbar) return false;
-    return true;
 }
 
 template <typename R>
@@ -621,6 +676,13 @@ size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_
     if (elem_size == 4) return carve_solve_ws<float>(nullptr, T, B, n_alpha, nullptr) + chunked_ws_bytes_slack();
     return 0;
 }
+size_t dtmpc_step_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size) {
+    const size_t a = dtmpc_solve_workspace_bytes(T, B, n_alpha, elem_size);
+    if (a == 0) return 0;
+    // per chunk: sens_ws_rows(T) rows of whole tiles, aligned; chunks add at most one tile and one alignment each
+    return a + (size_t)sens_ws_rows(T) * (size_t)((B + 31) / 32 * 32 + 32 * MAX_CHUNKS) * (size_t)elem_size +
+           256 * (size_t)MAX_CHUNKS;
+}
 uint64_t dtmpc_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size) {
     if (T < 1 || B < 0) return 0;
@@ -641,6 +703,12 @@ size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size)
                                   void *stream) {                                                                     \
         if (!aux || !aio) return fail(DTMPC_E_BADARG, "tube solve needs the auxiliary OCP");                          \
         return solve_impl<R>(env, nom, aux, B, nio, aio, ws, ws_bytes, stream);                                       \
+    }                                                                                                                 \
+    int dtmpc_tube_step_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,         \
+                                 const dtmpc_solve_io *nio, const dtmpc_solve_io *aio, const dtmpc_sens_io *sa,       \
+                                 const dtmpc_sens_io *sn, void *ws, size_t ws_bytes, void *stream) {                  \
+        if (!aux || !aio || !sa) return fail(DTMPC_E_BADARG, "tube step needs the auxiliary OCP and sens_aux");       \
+        return solve_impl<R>(env, nom, aux, B, nio, aio, ws, ws_bytes, stream, sa, sn, true);                         \
     }                                                                                                                 \
     int dtmpc_sensitivity_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_sens_io *io,    \
                                    void *ws, size_t ws_bytes, void *stream) {                                         \

@@ -13,7 +13,7 @@ namespace dtmpc {
 
 template <typename R> struct SensArgs {
     const R *X, *V, *theta, *target, *Xref, *Uref, *gx, *gu, *Xbar;
-    long long theta_stride, target_stride, xref_row;
+    long long theta_stride, target_stride, xref_row, gx_row;
     R *dX, *dV, *dL, *g_theta, *gXref, *gUref, *loss;
     int *status;
 };
@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     load_theta(th, a.theta + i * a.theta_stride, P.ocp);
     const R *X = a.X + i * (4LL * (T + 1));
     const R *V = a.V + i * (2LL * T);
-    const R *gxp = a.gx ? a.gx + i * (4LL * (T + 1)) : nullptr;
+    const int gxr = (int)a.gx_row;  // 4, or 3: no barrier-state component
+    const R *gxp = a.gx ? a.gx + i * ((long long)gxr * (T + 1)) : nullptr;
     const R *gup = a.gu ? a.gu + i * (2LL * T) : nullptr;
     const R *Xb = a.Xbar ? a.Xbar + i * (4LL * (T + 1)) : nullptr;
     const R gam = th.gamma, dt = E.dt;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     // upper-level gradient at step k: caller-supplied, or the tracking loss 2(x - xbar), 2b (core/tube_mpc.py:932-944)
     auto upper_gx = [&](int k, R px, R py, R pt, R pb, R &g0, R &g1, R &g2, R &g3) {
         if (gxp) {
-            g0 = gxp[4 * k]; g1 = gxp[4 * k + 1]; g2 = gxp[4 * k + 2]; g3 = gxp[4 * k + 3];
+            g0 = gxp[gxr * k]; g1 = gxp[gxr * k + 1]; g2 = gxp[gxr * k + 2]; g3 = gxr == 4 ? gxp[4 * k + 3] : R(0);
         } else {
             g0 = R(2) * (px - Xb[4 * k]);
             g1 = R(2) * (py - Xb[4 * k + 1]);

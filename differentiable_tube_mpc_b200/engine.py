@@ -48,6 +48,7 @@ class BatchedTubeMPC:
         self.trace = trace
         self.workspace = ops.Workspace(self.device)
         self.timers: Optional[Dict[str, list]] = None   # filled with CUDA events when enabled (bench.py)
+        self.unfused = False                            # True: separate library calls per stage (per-stage timers)
 
     @property
     def launches(self) -> int:
@@ -86,11 +87,9 @@ class BatchedTubeMPC:
 
         return _T()
 
-    def step(self, x0_nom: Tensor, x0_aux: Tensor, Vn_init: Tensor, Va_init: Tensor, theta_nom: Tensor,
-             theta_aux: Tensor, target: Optional[Tensor] = None, full: Optional[bool] = None) -> TubeStep:
-        """All tensors on self.device: x0_* [B,4], V*_init [B,T,2], theta_* [12] or [B,12] (constrained values)."""
+    def _step_unfused(self, x0_nom, x0_aux, Vn_init, Va_init, theta_nom, theta_aux, target, full):
+        """The same step as separate library calls (solve, sensitivity, sensitivity): per-section timing, custom target."""
         p = self.problem
-        full = (p.mode == "full") if full is None else full
         with self._timed("tube_solve"):
             rn, ra = ops.tube_solve_batched(p.system, p.nominal, p.auxiliary, x0_nom, x0_aux, Vn_init, Va_init,
                                             theta_nom, theta_aux, target=target, gains=self.gains, trace=self.trace,
@@ -100,7 +99,6 @@ class BatchedTubeMPC:
                                              U_ref=rn.V, want_grads=True, want_ref_grads=full, status=rn.status,
                                              workspace=self.workspace)
         sn = None
-        g_nom_sum = None
         if full:
             B, T = rn.X.shape[0], rn.V.shape[1]
             # upper gradients of the nominal problem: [dL/dx_ref, 0] and dL/du_ref (core/tube_mpc.py:520-535)
@@ -109,6 +107,22 @@ class BatchedTubeMPC:
                 sn = ops.ddp_sensitivity_batched(p.system, p.nominal, rn.X, rn.V, theta_nom, upper_grad_x=gx,
                                                  upper_grad_u=sa.g_uref, target=target, want_grads=True,
                                                  status=rn.status, workspace=self.workspace)
+        return rn, ra, sa, sn
+
+    def step(self, x0_nom: Tensor, x0_aux: Tensor, Vn_init: Tensor, Va_init: Tensor, theta_nom: Tensor,
+             theta_aux: Tensor, target: Optional[Tensor] = None, full: Optional[bool] = None) -> TubeStep:
+        """All tensors on self.device: x0_* [B,4], V*_init [B,T,2], theta_* [12] or [B,12] (constrained values)."""
+        p = self.problem
+        full = (p.mode == "full") if full is None else full
+        if target is None and not self.unfused:
+            # one library call: every chunk of the batch runs solves and sensitivity sweeps on its own stream
+            with self._timed("tube_step"):
+                rn, ra, sa, sn = ops.tube_step_batched(p.system, p.nominal, p.auxiliary, x0_nom, x0_aux, Vn_init, Va_init,
+                                                       theta_nom, theta_aux, full=full, gains=self.gains,
+                                                       trace=self.trace, workspace=self.workspace)
+        else:
+            rn, ra, sa, sn = self._step_unfused(x0_nom, x0_aux, Vn_init, Va_init, theta_nom, theta_aux, target, full)
+        g_nom_sum = None
         with self._timed("reduce"):
             g_aux_sum = ops.reduce_columns(torch.cat([sa.g_theta, sa.loss.view(-1, 1)], dim=1), self.workspace)
             if full:

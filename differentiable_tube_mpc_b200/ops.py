@@ -208,6 +208,70 @@ def tube_solve_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec,
     return SolveResult(**on), SolveResult(**oa)
 
 
+def tube_step_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec, x0_nom: Tensor, x0_aux: Tensor,
+                      Vn_init: Tensor, Va_init: Tensor, theta_nom: Tensor, theta_aux: Tensor, *, full: bool,
+                      target: Optional[Tensor] = None, gains: bool = False, trace: bool = False,
+                      workspace: Optional[Workspace] = None):
+    """One closed-loop step in one library call (`dtmpc_tube_step_*`): nominal solve, auxiliary solve, auxiliary
+    sensitivity + gradients with the built-in tracking loss, and (full = True) the nominal sensitivity + gradients
+    driven by dL/dx_ref, dL/du_ref of the auxiliary sweep (core/tube_mpc.py:844-976, :305-602).  Same results, bit for
+    bit, as tube_solve_batched + ddp_sensitivity_batched (x2); every chunk of the batch runs the whole chain on its own
+    stream.  Returns (nominal, auxiliary, sens_aux, sens_nom or None)."""
+    L = _lib.load()
+    dtype, device = x0_nom.dtype, x0_nom.device
+    sfx = _suffix(dtype)
+    B, T = int(x0_nom.shape[0]), int(nominal.ilqr.horizon)
+    x0_nom = _chk(x0_nom, (B, 4), dtype, "x0_nom")
+    x0_aux = _chk(x0_aux, (B, 4), dtype, "x0_aux")
+    Vn_init = _chk(Vn_init, (B, T, 2), dtype, "Vn_init")
+    Va_init = _chk(Va_init, (B, T, 2), dtype, "Va_init")
+    theta_nom, tsn = _theta_arg(theta_nom, B, dtype)
+    theta_aux, tsa = _theta_arg(theta_aux, B, dtype)
+    if target is None:
+        target = _const_tensor(system.y_target, dtype, device)
+    target, gs = _target_arg(target, B, dtype)
+    on = _alloc_solve(B, T, nominal.ilqr.max_iter, dtype, device, gains, trace)
+    oa = _alloc_solve(B, T, auxiliary.ilqr.max_iter, dtype, device, gains, trace, status=on["status"])
+    ion, ioa = _lib.SolveIO(), _lib.SolveIO()
+    _fill_io(ion, x0_nom, Vn_init, theta_nom, tsn, target, gs, None, None, on)
+    _fill_io(ioa, x0_aux, Va_init, theta_aux, tsa, None, 0, None, None, oa)
+    rn, ra = SolveResult(**on), SolveResult(**oa)
+
+    def new_sens(X, V):
+        return SensitivityResult(delta_X=torch.empty_like(X), delta_V=torch.empty_like(V), delta_lambda=torch.empty_like(X),
+                                 g_theta=torch.empty(B, _lib.NTHETA, dtype=dtype, device=device))
+
+    sa = new_sens(ra.X, ra.V)
+    sa.loss = torch.empty(B, dtype=dtype, device=device)
+    isa = _lib.SensIO()
+    isa.X, isa.V, isa.theta, isa.theta_stride = _ptr(ra.X), _ptr(ra.V), _ptr(theta_aux), tsa
+    isa.Xbar, isa.Xref, isa.Uref, isa.xref_row = _ptr(rn.X), _ptr(rn.X), _ptr(rn.V), 4
+    isa.dX, isa.dV, isa.dL, isa.g_theta = _ptr(sa.delta_X), _ptr(sa.delta_V), _ptr(sa.delta_lambda), _ptr(sa.g_theta)
+    isa.loss, isa.status = _ptr(sa.loss), _ptr(rn.status)
+    sn, isn = None, None
+    if full:
+        sa.g_xref = torch.empty(B, T + 1, 3, dtype=dtype, device=device)
+        sa.g_uref = torch.empty(B, T, 2, dtype=dtype, device=device)
+        isa.gXref, isa.gUref = _ptr(sa.g_xref), _ptr(sa.g_uref)
+        sn = new_sens(rn.X, rn.V)
+        isn = _lib.SensIO()
+        isn.X, isn.V, isn.theta, isn.theta_stride = _ptr(rn.X), _ptr(rn.V), _ptr(theta_nom), tsn
+        isn.target, isn.target_stride = _ptr(target), gs
+        isn.gx, isn.gx_row, isn.gu = _ptr(sa.g_xref), 3, _ptr(sa.g_uref)   # [dL/dx_ref, 0] (core/tube_mpc.py:520-535)
+        isn.dX, isn.dV, isn.dL, isn.g_theta = _ptr(sn.delta_X), _ptr(sn.delta_V), _ptr(sn.delta_lambda), _ptr(sn.g_theta)
+        isn.status = _ptr(rn.status)
+    env_c, n_c, a_c = system.to_c(), nominal.to_c(), auxiliary.to_c()
+    ws = workspace or default_workspace(device)
+    with torch.cuda.device(device):
+        nbytes = L.dtmpc_step_workspace_bytes(T, B, max(n_c.n_alpha, a_c.n_alpha), x0_nom.element_size())
+        buf = ws.get("step", nbytes)
+        rc = getattr(L, f"dtmpc_tube_step_{sfx}")(C.byref(env_c), C.byref(n_c), C.byref(a_c), B, C.byref(ion),
+                                                  C.byref(ioa), C.byref(isa), C.byref(isn) if isn is not None else None,
+                                                  _ptr(buf), buf.numel(), _stream())
+    _lib.check(rc, "dtmpc_tube_step")
+    return rn, ra, sa, sn
+
+
 @dataclass
 class SensitivityResult:
     """Batched counterpart of core/ddp.py:310-314 plus the fused IFT accumulation."""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DTMPC_ABI_VERSION 1
+#define DTMPC_ABI_VERSION 2
 #define DTMPC_MAX_OBS 16
 #define DTMPC_MAX_ALPHAS 8
 #define DTMPC_NTHETA 12
@@ -124,6 +124,8 @@ typedef struct dtmpc_sens_io {
     void *gXref, *gUref;            /* real [B,T+1,3], [B,T,2] out, optional                          */
     void *loss;                     /* real [B] out, optional (built-in loss only)                   */
     int32_t *status;                /* [B] in/out, optional: DTMPC_ST_NONFINITE is OR-ed in          */
+    int64_t gx_row;                 /* row length of gx: 4 (0 means 4) or 3 (no barrier-state        */
+                                    /* component: lets gXref of one sweep drive the next one)        */
 } dtmpc_sens_io;
 
 int dtmpc_abi_version(void);
@@ -135,6 +137,7 @@ uint64_t dtmpc_kernel_launches(void);
  * n_alpha = number of line-search step sizes (the larger of the two OCPs for a tube solve). */
 size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size);
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size);
+size_t dtmpc_step_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size);
 size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size);
 
 /* ilqr_solve for B instances -- reference core/ddp.py:102-307 (clamp, rollout, <= max_iter x
@@ -153,6 +156,19 @@ int dtmpc_tube_solve_f64(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc
 int dtmpc_tube_solve_f32(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,
                          const dtmpc_solve_io *nom_io, const dtmpc_solve_io *aux_io, void *workspace,
                          size_t workspace_bytes, void *stream);
+
+/* One closed-loop step of the reference in one call (core/tube_mpc.py:844-976 paper mode, :305-602 full mode):
+ * nominal solve, auxiliary solve, auxiliary sensitivity + gradients (sens_aux), and -- when sens_nom is not NULL --
+ * the nominal sensitivity + gradients.  The sens_io buffers are the caller's as for dtmpc_sensitivity_*: sens_aux->X/V
+ * = aux_io->X/V, Xref/Uref/Xbar = nom_io->X/V (xref_row 4); sens_nom->X/V = nom_io->X/V, gx = sens_aux->gXref with
+ * gx_row 3, gu = sens_aux->gUref.  Every chunk of the batch runs its whole chain on its own stream, so the
+ * sensitivity sweeps of one chunk overlap the solves of the others.  workspace: dtmpc_step_workspace_bytes. */
+int dtmpc_tube_step_f64(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,
+                        const dtmpc_solve_io *nom_io, const dtmpc_solve_io *aux_io, const dtmpc_sens_io *sens_aux,
+                        const dtmpc_sens_io *sens_nom, void *workspace, size_t workspace_bytes, void *stream);
+int dtmpc_tube_step_f32(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,
+                        const dtmpc_solve_io *nom_io, const dtmpc_solve_io *aux_io, const dtmpc_sens_io *sens_aux,
+                        const dtmpc_sens_io *sens_nom, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ddp_sensitivity (reference core/ddp.py:317-427) fused with the IFT accumulation
  * (reference core/ift.py:35-92, closed forms; paper mode core/tube_mpc.py:965-976). */

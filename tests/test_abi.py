@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(lib):
     exported = set(re.findall(r"\bT (dtmpc_[a-z0-9_]+)", out))
     missing = [f for f in _declared_functions() if f not in exported]
     assert not missing, missing
-    assert lib.dtmpc_abi_version() == 1
+    assert lib.dtmpc_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_native():

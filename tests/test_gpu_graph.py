@@ -76,7 +76,7 @@ def test_launch_counter_counts_kernels():
     eng.step(*args, full=False)
     torch.cuda.synchronize()
     # init + max_iter x (ric, fwd, commit) per OCP, one sensitivity sweep, two reduction kernels
-    expect = (1 + 3 * p.nominal.ilqr.max_iter) + (1 + 3 * p.auxiliary.ilqr.max_iter) + 1 + 2
+    expect = (1 + 3 * p.nominal.ilqr.max_iter) + (1 + 3 * p.auxiliary.ilqr.max_iter) + 1 + 2   # B = 512: one chunk
     assert ops.kernel_launches() - n0 == expect
 
 
@@ -131,3 +131,26 @@ def test_double_buffered_steps_overlap_copies_without_changing_results():
             assert torch.equal(g, w), i
     with pytest.raises(AssertionError):
         db.run()
+
+
+@pytest.mark.parametrize("mode", ["paper", "full"])
+def test_fused_tube_step_is_the_separate_calls(mode):
+    """dtmpc_tube_step (solves + sensitivity sweeps per chunk, one library call) against dtmpc_tube_solve followed by
+    dtmpc_sensitivity (x2): the same bits, gradients included."""
+    eng, args = _problem(16384 + 40, 10, mode)
+    full = mode == "full"
+    fused = eng.step(*args, full=full)
+    eng.unfused = True
+    sep = eng.step(*args, full=full)
+    eng.unfused = False
+    torch.cuda.synchronize()
+    _same(fused, sep)
+    for a, b in ((fused.sens_aux, sep.sens_aux), (fused.sens_nom, sep.sens_nom)):
+        if a is None:
+            assert b is None
+            continue
+        assert torch.equal(a.delta_X, b.delta_X) and torch.equal(a.delta_V, b.delta_V)
+        assert torch.equal(a.delta_lambda, b.delta_lambda) and torch.equal(a.g_theta, b.g_theta)
+    if full:
+        assert torch.equal(fused.sens_aux.g_xref, sep.sens_aux.g_xref)
+        assert torch.equal(fused.sens_aux.g_uref, sep.sens_aux.g_uref)

@@ -96,22 +96,6 @@ __host__ __device__ inline long long tile_off(long long s, long long rows) { ret
 
 template <typename R> struct RefPt { R x0, x1, x2, u0, u1; };
 
-// L2 prefetch hint (no register, no dependency): the serial sweeps touch a fresh set of rows every step, and with few
-// resident warps nothing else hides the DRAM latency of those rows.
-#ifndef DTMPC_L2_PREFETCH
-#define DTMPC_L2_PREFETCH 0  // measured: 3 steps ahead costs 3-9 % (B = 65,536), the hints only add issue slots
-#endif
-template <typename R> __device__ __forceinline__ void prefetch_l2(const R *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// Asynchronous global -> shared copy of one element (LDGSTS): no destination register, so a sweep can keep the inputs
-// of several future steps in flight without paying for them in occupancy.  Every thread reads back only what it
-// copied itself, so cp.async.wait_group is all the synchronisation there is.
-template <typename R> __device__ __forceinline__ void cp_async_elem(R *smem_dst, const R *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(sizeof(R)) : "memory");
-}
 // Bulk asynchronous copy (the TMA engine without a tensor map): one thread moves a contiguous block global -> shared
 // and the bytes are accounted on an mbarrier; consumers wait on the barrier's phase.  PTX ISA 8.x, sm_90+.
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -138,8 +122,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename R>
 __device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *rk, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {

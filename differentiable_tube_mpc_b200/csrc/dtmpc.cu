@@ -351,6 +351,10 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
     ChunkStreams *cs = n_chunks > 1 ? chunk_streams() : nullptr;
     if (!cs) n_chunks = 1;
     const long long per = chunk_size(B, n_chunks);
+    // the pool's fork/done events are shared by every call on this device: enqueue one chunked call at a time
+    static std::mutex enqueue_mu;
+    std::unique_lock<std::mutex> enqueue_lock(enqueue_mu, std::defer_lock);
+    if (n_chunks > 1) enqueue_lock.lock();
     if (n_chunks > 1) {
         cudaError_t e = cudaEventRecord(cs->fork, user);
         if (e != cudaSuccess) return cuda_fail(e, "chunk fork");

@@ -128,6 +128,8 @@ typedef struct dtmpc_sens_io {
                                     /* component: lets gXref of one sweep drive the next one)        */
 } dtmpc_sens_io;
 
+/* Thread safety: entry points may be called from several host threads (errors are thread-local; chunked solves
+ * serialise their enqueue on an internal lock).  All work is asynchronous on the caller's stream. */
 int dtmpc_abi_version(void);
 const char *dtmpc_last_error(void);
 /* Number of CUDA kernels this library has enqueued in this process so far (all entry points, all streams). */

@@ -101,3 +101,36 @@ def test_empty_batch_and_bad_arguments():
     with pytest.raises((ValueError, TypeError, RuntimeError)):
         ops.tube_solve_batched(prob.system, prob.nominal, prob.auxiliary, z(3, 4), z(3, 4), z(3, 4, 2), z(3, 5, 2),
                                cu(prob.theta_nom0), cu(prob.theta_aux0))
+
+
+def test_closed_form_weight_gradients_cross_check(oracle):
+    """core/gradients.py:27-87 (defined but unused by the reference) restated in gradients.py, against the weight
+    entries of the fused CUDA accumulation, for both OCPs of a full-mode step."""
+    from differentiable_tube_mpc_b200 import TubeProblem, default_dubins_config, ops
+    from differentiable_tube_mpc_b200.gradients import grads_auxiliary_from_deltas, grads_nominal_from_deltas
+
+    cfg = default_dubins_config()
+    cfg["system"]["horizon_N"] = 15
+    prob = TubeProblem.from_config(cfg, mode="full")
+    B, T = 96, 15
+    x, xb = make_instances(B, 77, cfg)
+    th_bar, th = prob.make_thetas(DEV, torch.float64)
+    thn = th_bar.constrained().detach().expand(B, 12).contiguous()
+    tha = th.constrained().detach().expand(B, 12).contiguous()
+    z = torch.zeros(B, 1, dtype=torch.float64, device=DEV)
+    u = torch.zeros(B, 2, dtype=torch.float64, device=DEV)
+    b0n = ops.primitives_batched(prob.system, prob.nominal, torch.cat([cu(xb), z], 1), u, thn)["b0"]
+    b0a = ops.primitives_batched(prob.system, prob.auxiliary, torch.cat([cu(x), z], 1), u, tha)["b0"]
+    V0 = torch.zeros(B, T, 2, dtype=torch.float64, device=DEV)
+    rn, ra, sa, sn = ops.tube_step_batched(prob.system, prob.nominal, prob.auxiliary, torch.cat([cu(xb), b0n.view(-1, 1)], 1),
+                                           torch.cat([cu(x), b0a.view(-1, 1)], 1), V0, V0, thn, tha, full=True)
+    ga = grads_auxiliary_from_deltas(X_hat=ra.X, U=ra.V, dX=sa.delta_X, dU=sa.delta_V, X_ref=rn.X, U_ref=rn.V)
+    gn = grads_nominal_from_deltas(X_hat=rn.X, U=rn.V, dX=sn.delta_X, dU=sn.delta_V,
+                                   target_x=cu(np.asarray(prob.system.y_target)))
+    for g, s, r in ((ga, sa, ra), (gn, sn, rn)):
+        k = s.g_theta
+        scale = k[:, :9].abs().max(dim=1).values.clamp_min(1e-30)
+        qb_T = 2.0 * r.X[:, -1, 3] * s.delta_X[:, -1, 3]
+        for got, want in ((g.Q_diag, k[:, 0:3]), (g.R_diag, k[:, 3:5]), (g.Qf_diag, k[:, 5:8]),
+                          ((g.q_b + qb_T).view(-1, 1), k[:, 8:9])):
+            assert float(((got - want).abs().max(dim=1).values / scale).max()) < 1e-12

@@ -1,4 +1,5 @@
-"""Diagnostic: per-step and per-kernel CUDA-event times of the bench workload (not a bench; prints a table)."""
+"""Diagnostic: per-step and per-library-call CUDA-event times of the bench workload (not a bench; prints a table:
+rows tube_step = dtmpc_tube_step (both solves + sensitivity sweeps), reduce)."""
 import argparse, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -174,7 +174,8 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
             const int nc = fwd_candidates_per_thread(P.n_eval);
             const int ny = (P.n_eval + nc - 1) / nc;
             const dim3 blk(32, ny > 0 ? ny : 1);
-            if (nc == 1 && fixed_nobs == 5) fwd_kernel<R, 1, 5><<<gFwd, blk, 0, st>>>(P);
+            if (nc == 1 && fixed_nobs == 5 && P.use_ref) fwd_kernel<R, 1, 5, 1><<<gFwd, blk, 0, st>>>(P);
+            else if (nc == 1 && fixed_nobs == 5) fwd_kernel<R, 1, 5, 0><<<gFwd, blk, 0, st>>>(P);
             else if (nc == 1) fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
             else if (nc == 2) fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
             else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);

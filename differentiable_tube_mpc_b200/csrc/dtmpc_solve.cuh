@@ -123,9 +123,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <typename R>
+// UR: -1 = P.use_ref decides at run time, 0 / 1 = fixed at compile time (the line search is instantiated for both)
+template <typename R, int UR = -1>
 __device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *rk, bool with_u, R t0, R t1, R t2, RefPt<R> &r) {
-    if (P.use_ref) {  // rk = ws.ref + tile_off(i, ref_rows(T)) + EL(k, RR, 0): the reference of step k
+    if (UR < 0 ? P.use_ref != 0 : UR != 0) {  // rk = ws.ref + tile_off(i, ref_rows(T)) + EL(k, RR, 0): the reference of step k
         r.x0 = rk[0 * 32];
         r.x1 = rk[1 * 32];
         r.x2 = rk[2 * 32];
@@ -392,8 +393,11 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 // candidates.  The costs meet in shared memory; warp 0 picks the winner (strict '<' in list order), applies the
 // tolerance break to the accepted costs and records the decision.
 // ---------------------------------------------------------------------------------------------------------------
+// Register cap of the line search: the kernel needs ~90 registers unconstrained; 72 costs ~60 B of spills per thread
+// but fits 7 CTAs of 4 warps per SM instead of 5.  Same-box sweep (tube step, B = 65,536, full / paper mode):
+// 96: 20.0 / 15.1 ms, 80: 19.7 / 14.4, 76: 19.8 / 14.5, 72: 19.4 / 14.6, 64: 19.5 / 14.5.
 #ifndef DTMPC_FWD_MAXNREG
-#define DTMPC_FWD_MAXNREG 96
+#define DTMPC_FWD_MAXNREG 72
 #endif
 // The per-instance parameters a rollout step needs (12 values) are the same for every candidate warp of the CTA and
 // constant over the sweep: parked in shared memory and re-read each step they cost 12 LDS instead of ~24 registers.
@@ -432,7 +436,7 @@ template <typename R> __device__ __forceinline__ void theta_fetch_jac(const R *s
 }
 constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 
-template <typename R, int NC, int NOBS = -1>
+template <typename R, int NC, int NOBS = -1, int UR = -1>
 __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     __shared__ R sJ[DTMPC_MAX_ALPHAS * 32];
@@ -457,7 +461,7 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
     Theta<R> th;
     load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
     R t0 = R(0), t1 = R(0), t2 = R(0);
-    if (!P.use_ref) {
+    if (UR < 0 ? !P.use_ref : UR == 0) {
         const R *tp = P.io.target + i * P.io.target_stride;
         t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
     }
@@ -545,7 +549,7 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         const R k0 = gp[8 * 32], k1 = gp[9 * 32];
 #endif
         RefPt<R> r;
-        ref_at(P, rp, true, t0, t1, t2, r);
+        ref_at<R, UR>(P, rp, true, t0, t1, t2, r);
         xp += TR * 32;  // one running pointer per stream: every load is pointer + immediate
         gp += GR * 32;
         rp += RR * 32;
@@ -571,7 +575,7 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
         step_multi<R, NC, NOBS>(E, tk, x, u0, u1);
     }
     RefPt<R> r;
-    ref_at(P, rp, false, t0, t1, t2, r);
+    ref_at<R, UR>(P, rp, false, t0, t1, t2, r);
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         J[q] += terminal_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, r.x0, r.x1, r.x2);

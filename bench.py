@@ -145,7 +145,7 @@ class ClockSampler:
 def traffic_from_profile():
     """DRAM bytes (read + write) per launch of the largest kernel, from the committed ncu --set full capture."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01f_traffic.json")))
         return {"kernel": t["kernel"], "bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
     except Exception:
         return None

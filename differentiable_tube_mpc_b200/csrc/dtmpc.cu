@@ -135,7 +135,7 @@ bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
 
 // One batched OCP: init, max_iter x (Riccati, line search + selection, commit).  Everything is
 // stream-ordered; the host never waits, so all max_iter iterations are enqueued and the ones that find the
-// active list empty return at once.
+// slots all vacated return at once.
 // candidates rolled out per thread of the line-search kernel (DTMPC_FWD_NC overrides, for tuning)
 int fwd_candidates_per_thread(int n_eval) {
     static int forced = -1;

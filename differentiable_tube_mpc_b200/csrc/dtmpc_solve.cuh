@@ -142,7 +142,7 @@ __device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *rk, boo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// init: V = clamp(V_init), X = rollout(x0, V)  (core/ddp.py:125-131); every instance enters the active list
+// init: V = clamp(V_init), X = rollout(x0, V)  (core/ddp.py:125-131); every instance starts in slot i
 // ---------------------------------------------------------------------------------------------------------------
 template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(const __grid_constant__ SolveParams<R> P) {
     const long long i = (long long)blockIdx.x * LS_BLOCK + threadIdx.x;

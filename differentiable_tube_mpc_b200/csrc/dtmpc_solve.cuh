@@ -696,11 +696,8 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
     const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
     // destinations: next slot (running) or the result tensors (stopping)
     R *Xn = P.ws.traj[P.parity ^ 1] + tile_off(jn, traj_rows(T));
-    R *Xo = P.io.X + i * (4LL * (T + 1));
-    R *Vo = P.io.V + i * (2LL * T);
-    R *Ko = P.io.K ? P.io.K + i * (8LL * T) : nullptr;
-    R *ko = P.io.kff ? P.io.kff + i * (2LL * T) : nullptr;
-    R *Ro = P.write_ref ? P.ws.ref + tile_off(i, ref_rows(T)) : nullptr;
+    // (the result pointers of a stopping instance are formed where they are used: held across the sweep they cost
+    // ten registers of every lane for the benefit of the few that stop)
 
     // state at the head of the segment: x_0, or the winner's checkpoint; and the old trajectory's state there
     R X0 = X[EL(k_lo, TR, 0)], X1 = X[EL(k_lo, TR, 1)], X2 = X[EL(k_lo, TR, 2)], X3 = X[EL(k_lo, TR, 3)];
@@ -711,8 +708,11 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
             Xn[EL(0, TR, 0)] = X0; Xn[EL(0, TR, 1)] = X1; Xn[EL(0, TR, 2)] = X2; Xn[EL(0, TR, 3)] = X3;
             Xn[EL(0, TR, 6)] = X[EL(0, TR, 6)]; Xn[EL(0, TR, 7)] = X[EL(0, TR, 7)];
         } else {
-            st4(Xo, X0, X1, X2, X3);
-            if (Ro) { Ro[EL(0, RR, 0)] = X0; Ro[EL(0, RR, 1)] = X1; Ro[EL(0, RR, 2)] = X2; }
+            st4(P.io.X + i * (4LL * (T + 1)), X0, X1, X2, X3);
+            if (P.write_ref) {
+                R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
+                Ro[EL(0, RR, 0)] = X0; Ro[EL(0, RR, 1)] = X1; Ro[EL(0, RR, 2)] = X2;
+            }
             if (P.io.iters) P.io.iters[i] = P.ws.it[i];
         }
     } else if (!copy) {
@@ -764,14 +764,16 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
             xn[(TR + 7) * 32] = gy;
             xn += TR * 32;
         } else {
-            st2(Vo + 2 * k, u0, u1);
-            st4(Xo + 4 * (k + 1), x.px, x.py, x.th, x.b);
-            if (Ko) {
-                st4(Ko + 8 * k, K00, K01, K02, K03);
-                st4(Ko + 8 * k + 4, K10, K11, K12, K13);
+            st2(P.io.V + i * (2LL * T) + 2 * k, u0, u1);
+            st4(P.io.X + i * (4LL * (T + 1)) + 4 * (k + 1), x.px, x.py, x.th, x.b);
+            if (P.io.K) {
+                R *Ko = P.io.K + i * (8LL * T) + 8 * k;
+                st4(Ko, K00, K01, K02, K03);
+                st4(Ko + 4, K10, K11, K12, K13);
             }
-            if (ko) st2(ko + 2 * k, k0, k1);
-            if (Ro) {
+            if (P.io.kff) st2(P.io.kff + i * (2LL * T) + 2 * k, k0, k1);
+            if (P.write_ref) {
+                R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
                 Ro[EL(k + 1, RR, 0)] = x.px;
                 Ro[EL(k + 1, RR, 1)] = x.py;
                 Ro[EL(k + 1, RR, 2)] = x.th;

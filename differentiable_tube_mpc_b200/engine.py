@@ -178,12 +178,21 @@ class DoubleBufferedSteps:
             out = db.run()
     """
 
-    def __init__(self, eng: "BatchedTubeMPC", *args, full=None):
-        self.steps = [GraphedStep(eng, *args, full=full) for _ in range(2)]
+    def __init__(self, eng: "BatchedTubeMPC", *args, full=None, overlap_steps: bool = False):
+        """overlap_steps = True gives the second buffer its own scratch and each buffer its own compute stream, so two
+        consecutive (independent) steps may be in flight at once: the low-occupancy head (initial rollouts) and tail
+        (sensitivity sweeps) of one step fill with the other's line search.  Only for streams of independent batches;
+        a closed loop needs step i before it can start step i+1."""
         self.device = eng.device
+        self.overlap = bool(overlap_steps)
+        engs = [eng, BatchedTubeMPC(eng.problem, device=eng.device, dtype=eng.dtype, gains=eng.gains, trace=eng.trace)
+                if self.overlap else eng]
+        self.steps = [GraphedStep(e, *args, full=full) for e in engs]
         self.copy_stream = torch.cuda.Stream(device=eng.device)
+        self.compute = [torch.cuda.Stream(device=eng.device) for _ in range(2)] if self.overlap else None
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.done = [None, None]
+        self.consumed = [None, None]
         self.n_prefetched = 0
         self.n_run = 0
 
@@ -193,19 +202,40 @@ class DoubleBufferedSteps:
         with torch.cuda.stream(self.copy_stream):
             if self.done[slot] is not None:            # the graph that last read these static inputs has finished
                 self.copy_stream.wait_event(self.done[slot])
+            else:                                      # first use: the static tensors were made on the caller's stream
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
             for k, v in host_inputs.items():
                 self.steps[slot].static[k].copy_(v, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
         self.n_prefetched += 1
 
     def run(self) -> TubeStep:
+        """Replays the next step; the results are ordered on the CALLER's stream (read them there)."""
         slot = self.n_run % 2
         assert self.n_prefetched > self.n_run, "run() without a prefetch()"
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(self.ready[slot])
-        out = self.steps[slot]()
-        self.done[slot] = torch.cuda.Event()
-        self.done[slot].record(cur)
+        if self.overlap:
+            # the caller has by now enqueued its reads of the PREVIOUS step's results on its stream: mark them, so that
+            # the graph that overwrites that buffer two steps later waits for them (and for nothing else on `cur`)
+            if self.n_run > 0:
+                self.consumed[1 - slot] = torch.cuda.Event()
+                self.consumed[1 - slot].record(cur)
+            cs = self.compute[slot]
+            if self.consumed[slot] is not None:
+                cs.wait_event(self.consumed[slot])
+            else:
+                cs.wait_stream(cur)                    # first use of this buffer
+            cs.wait_event(self.ready[slot])
+            with torch.cuda.stream(cs):
+                out = self.steps[slot]()
+            self.done[slot] = torch.cuda.Event()
+            self.done[slot].record(cs)
+            cur.wait_event(self.done[slot])
+        else:
+            cur.wait_event(self.ready[slot])
+            out = self.steps[slot]()
+            self.done[slot] = torch.cuda.Event()
+            self.done[slot].record(cur)
         self.n_run += 1
         return out
 

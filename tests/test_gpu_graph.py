@@ -104,7 +104,8 @@ np.savez(sys.argv[1], nX=st.nominal.X.cpu().numpy(), aX=st.auxiliary.X.cpu().num
             assert np.array_equal(outs[0][k], o[k]), k
 
 
-def test_double_buffered_steps_overlap_copies_without_changing_results():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_double_buffered_steps_overlap_copies_without_changing_results(overlap):
     from differentiable_tube_mpc_b200.engine import DoubleBufferedSteps
 
     B, T = 4096, 10
@@ -119,14 +120,16 @@ def test_double_buffered_steps_overlap_copies_without_changing_results():
     host = [{k: v.cpu().pin_memory() for k, v in zip(names, a)} for a in variants]
     want = [eng.step(*a, full=False) for a in variants]
     want = [(w.auxiliary.X.clone(), w.loss.clone(), w.g_aux_sum.clone()) for w in want]
-    db = DoubleBufferedSteps(eng, *args, full=False)
+    db = DoubleBufferedSteps(eng, *args, full=False, overlap_steps=overlap)   # overlap: two steps in flight
     db.prefetch(**host[0])
+    gots = []
     for i in range(4):
         if i + 1 < 4:
             db.prefetch(**host[i + 1])
         out = db.run()
-        got = (out.auxiliary.X.clone(), out.loss.clone(), out.g_aux_sum.clone())
-        torch.cuda.synchronize()
+        gots.append((out.auxiliary.X.clone(), out.loss.clone(), out.g_aux_sum.clone()))   # read on the caller's stream
+    torch.cuda.synchronize()       # no host synchronisation inside the loop: steps and copies really overlap
+    for i, got in enumerate(gots):
         for g, w in zip(got, want[i]):
             assert torch.equal(g, w), i
     with pytest.raises(AssertionError):

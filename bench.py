@@ -386,11 +386,26 @@ def main():
 
     # warm-up: at least W (>= 3) steps AND ~2 s of load -- the first launches pay lazy module loading and the SM
     # clocks need a few hundred ms to ramp from idle (first two steps measured 2-9x slower than steady state)
+    # Every step ends in a collective when world > 1, so all ranks must run the SAME number of warm-up steps: the count
+    # that fills the warm-up time is derived from all-reduced timings, never from a rank's own clock.
     n_warm, t_warm = 0, time.perf_counter()
-    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_warm) < args.warmup_seconds:
+    for _ in range(max(args.warmup, 3)):
         device_steps(1)
         torch.cuda.synchronize()
         n_warm += 1
+    t1 = time.perf_counter()
+    device_steps(2)
+    torch.cuda.synchronize()
+    n_warm += 2
+    est = torch.tensor([time.perf_counter() - t_warm, (time.perf_counter() - t1) / 2.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MIN)
+    spent, per_step = float(est[0]), max(float(est[1]), 1e-4)
+    n_extra = int(max(0.0, args.warmup_seconds - spent) / per_step)
+    for _ in range(n_extra):
+        device_steps(1)
+        n_warm += 1
+    torch.cuda.synchronize()
     # per-kernel-group durations (CUDA events around each library call, on the launching stream) and the number of
     # kernels one step launches: measured on the plain launch path, which is what the graph replays.  The plain path
     # pays ~190 host launches per chunk, so its first steps and any host hiccup inflate a section: median of 9.

@@ -162,7 +162,7 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     P.n_seg = T < MAX_SEG ? T : MAX_SEG;
     P.seg_len = (T + P.n_seg - 1) / P.n_seg;
     P.n_seg = (T + P.seg_len - 1) / P.seg_len;
-    // kernels with the obstacle count fixed at compile time exist for the reference scenario (5 circles, smooth-min)
+    // kernels with the obstacle count fixed at compile time (1..8 circles, smooth-min; the reference scenario has 5)
     static const bool allow_fixed = !getenv("DTMPC_NO_FIXED_NOBS");
     const int fixed_nobs = (allow_fixed && P.env.agg == DTMPC_AGG_SMOOTHMIN) ? P.env.n_obs : -1;
     P.parity = 0;
@@ -174,15 +174,31 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
             const int nc = fwd_candidates_per_thread(P.n_eval);
             const int ny = (P.n_eval + nc - 1) / nc;
             const dim3 blk(32, ny > 0 ? ny : 1);
-            if (nc == 1 && fixed_nobs == 5 && P.use_ref) fwd_kernel<R, 1, 5, 1><<<gFwd, blk, 0, st>>>(P);
-            else if (nc == 1 && fixed_nobs == 5) fwd_kernel<R, 1, 5, 0><<<gFwd, blk, 0, st>>>(P);
-            else if (nc == 1) fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
+            // obstacle counts 1..8 of a smooth-min environment have kernels with the count fixed at compile time
+#define DTMPC_FWD_CASE(N)                                                             \
+    case N:                                                                           \
+        if (P.use_ref) fwd_kernel<R, 1, N, 1><<<gFwd, blk, 0, st>>>(P);               \
+        else fwd_kernel<R, 1, N, 0><<<gFwd, blk, 0, st>>>(P);                         \
+        break;
+            if (nc == 1) {
+                switch (fixed_nobs) {
+                    DTMPC_FWD_CASE(1) DTMPC_FWD_CASE(2) DTMPC_FWD_CASE(3) DTMPC_FWD_CASE(4)
+                    DTMPC_FWD_CASE(5) DTMPC_FWD_CASE(6) DTMPC_FWD_CASE(7) DTMPC_FWD_CASE(8)
+                    default: fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
+                }
+            }
+#undef DTMPC_FWD_CASE
             else if (nc == 2) fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
             else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);
         }
         // the last iteration retires every instance still running
-        if (fixed_nobs == 5) commit_kernel<R, 5><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
-        else commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
+#define DTMPC_COMMIT_CASE(N) case N: commit_kernel<R, N><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P); break;
+        switch (fixed_nobs) {
+            DTMPC_COMMIT_CASE(1) DTMPC_COMMIT_CASE(2) DTMPC_COMMIT_CASE(3) DTMPC_COMMIT_CASE(4)
+            DTMPC_COMMIT_CASE(5) DTMPC_COMMIT_CASE(6) DTMPC_COMMIT_CASE(7) DTMPC_COMMIT_CASE(8)
+            default: commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
+        }
+#undef DTMPC_COMMIT_CASE
         P.parity ^= 1;
     }
     count_launches(1ull + 3ull * (unsigned long long)P.ocp.max_iter);

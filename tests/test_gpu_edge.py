@@ -1,6 +1,6 @@
 """GPU parity on the shapes the slot/tile/segment machinery could get wrong: horizons shorter than the number of commit
 segments, batches that are not whole tiles of 32, a single instance, step-size lists with one entry or with only
-alpha = 0, an obstacle count without a compile-time instantiation, no obstacles.  Checked against the CPU oracle."""
+alpha = 0, every kind of obstacle count (none, compile-time instantiated, generic).  Checked against the CPU oracle."""
 from dataclasses import replace
 
 import numpy as np
@@ -23,7 +23,10 @@ def _setup(oracle, T, B, seed, n_obs=None, alphas=None, max_iter=None):
     cfg = default_dubins_config()
     cfg["system"]["horizon_N"] = int(T)
     if n_obs is not None:
-        cfg["environment"]["obstacles"] = cfg["environment"]["obstacles"][:n_obs]
+        obs = list(cfg["environment"]["obstacles"])
+        while len(obs) < n_obs:      # extra circles far from every start state: more terms, same geometry nearby
+            obs.append({"center": [40.0 + 3.0 * len(obs), -30.0], "radius": 1.0})
+        cfg["environment"]["obstacles"] = obs[:n_obs]
     if alphas is not None:
         cfg["system"]["line_search_alphas"] = list(alphas)
     if max_iter is not None:
@@ -79,8 +82,9 @@ def test_degenerate_step_size_lists(oracle, alphas):
     _check(oracle, prob, env, nom, aux, x0n, x0a, 9)
 
 
-@pytest.mark.parametrize("n_obs", [0, 1, 3])
-def test_obstacle_counts_without_a_specialised_kernel(oracle, n_obs):
+@pytest.mark.parametrize("n_obs", [0, 1, 3, 8, 10])
+def test_obstacle_counts(oracle, n_obs):
+    """1..8 circles run kernels with the count fixed at compile time, 0 and 10 the generic ones."""
     prob, env, nom, aux, x0n, x0a = _setup(oracle, 12, 48, seed=31 + n_obs, n_obs=n_obs)
     _check(oracle, prob, env, nom, aux, x0n, x0a, 12)
 

@@ -323,7 +323,7 @@ def main():
     # --sequential keeps one step in flight; the JSON line always carries the sequential figure too.
     overlap = not (args.sequential or args.no_graph)
     dbuf = None if args.no_graph else DoubleBufferedSteps(eng, d_x0n, d_x0a, d_V0, d_V0, d_th_n, d_th_a, full=full,
-                                                          overlap_steps=overlap)
+                                                          overlap_steps=overlap, buffers=int(os.environ.get("DTMPC_BENCH_BUFFERS", "2")))
 
     def device_steps(n):     # inputs resident: the static tensors of the two buffers already hold them
         last = None
@@ -474,7 +474,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "launch_mode": "plain" if graphed is None else "cuda_graph_replay",
-                "steps_in_flight": 2 if overlap else 1,
+                "steps_in_flight": (dbuf.nb if overlap else 1),
                 "sequential": {"value": total * args.steps / (ms_seq * 1e-3), "unit": UNIT,
                                "ms_per_step": ms_seq / args.steps,
                                "note": "same K steps with one step in flight (each replay starts after the previous one)"},

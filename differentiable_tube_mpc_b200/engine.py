@@ -178,27 +178,28 @@ class DoubleBufferedSteps:
             out = db.run()
     """
 
-    def __init__(self, eng: "BatchedTubeMPC", *args, full=None, overlap_steps: bool = False):
+    def __init__(self, eng: "BatchedTubeMPC", *args, full=None, overlap_steps: bool = False, buffers: int = 2):
         """overlap_steps = True gives the second buffer its own scratch and each buffer its own compute stream, so two
         consecutive (independent) steps may be in flight at once: the low-occupancy head (initial rollouts) and tail
         (sensitivity sweeps) of one step fill with the other's line search.  Only for streams of independent batches;
         a closed loop needs step i before it can start step i+1."""
         self.device = eng.device
         self.overlap = bool(overlap_steps)
-        engs = [eng, BatchedTubeMPC(eng.problem, device=eng.device, dtype=eng.dtype, gains=eng.gains, trace=eng.trace)
-                if self.overlap else eng]
+        self.nb = nb = max(2, int(buffers))            # buffers = steps that may be in flight when overlap_steps
+        engs = [eng] + [BatchedTubeMPC(eng.problem, device=eng.device, dtype=eng.dtype, gains=eng.gains, trace=eng.trace)
+                        if self.overlap else eng for _ in range(nb - 1)]
         self.steps = [GraphedStep(e, *args, full=full) for e in engs]
         self.copy_stream = torch.cuda.Stream(device=eng.device)
-        self.compute = [torch.cuda.Stream(device=eng.device) for _ in range(2)] if self.overlap else None
-        self.ready = [torch.cuda.Event() for _ in range(2)]
-        self.done = [None, None]
-        self.consumed = [None, None]
+        self.compute = [torch.cuda.Stream(device=eng.device) for _ in range(nb)] if self.overlap else None
+        self.ready = [torch.cuda.Event() for _ in range(nb)]
+        self.done = [None] * nb
+        self.consumed = [None] * nb
         self.n_prefetched = 0
         self.n_run = 0
 
     def prefetch(self, **host_inputs) -> None:
-        slot = self.n_prefetched % 2
-        assert self.n_prefetched - self.n_run < 2, "at most two steps in flight"
+        slot = self.n_prefetched % self.nb
+        assert self.n_prefetched - self.n_run < self.nb, "every buffer already holds a step that has not run"
         with torch.cuda.stream(self.copy_stream):
             if self.done[slot] is not None:            # the graph that last read these static inputs has finished
                 self.copy_stream.wait_event(self.done[slot])
@@ -211,15 +212,16 @@ class DoubleBufferedSteps:
 
     def run(self) -> TubeStep:
         """Replays the next step; the results are ordered on the CALLER's stream (read them there)."""
-        slot = self.n_run % 2
+        slot = self.n_run % self.nb
         assert self.n_prefetched > self.n_run, "run() without a prefetch()"
         cur = torch.cuda.current_stream(self.device)
         if self.overlap:
             # the caller has by now enqueued its reads of the PREVIOUS step's results on its stream: mark them, so that
             # the graph that overwrites that buffer two steps later waits for them (and for nothing else on `cur`)
             if self.n_run > 0:
-                self.consumed[1 - slot] = torch.cuda.Event()
-                self.consumed[1 - slot].record(cur)
+                prev = (slot - 1) % self.nb
+                self.consumed[prev] = torch.cuda.Event()
+                self.consumed[prev].record(cur)
             cs = self.compute[slot]
             if self.consumed[slot] is not None:
                 cs.wait_event(self.consumed[slot])

@@ -76,6 +76,13 @@ def test_short_horizons_and_ragged_batches(oracle, T, B):
     _check(oracle, prob, env, nom, aux, x0n, x0a, T)
 
 
+@pytest.mark.parametrize("T,B", [(100, 24), (200, 12), (53, 40)])
+def test_long_and_odd_horizons(oracle, T, B):
+    """BASELINE config #4 horizons: segments of 20 / 40 steps, and a horizon the five segments do not divide."""
+    prob, env, nom, aux, x0n, x0a = _setup(oracle, T, B, seed=200 + T)
+    _check(oracle, prob, env, nom, aux, x0n, x0a, T)
+
+
 @pytest.mark.parametrize("alphas", [(1.0,), (0.0,), (0.3, 0.0), (0.0, 1.0, 0.5)])
 def test_degenerate_step_size_lists(oracle, alphas):
     prob, env, nom, aux, x0n, x0a = _setup(oracle, 9, 40, seed=7, alphas=alphas, max_iter=4)

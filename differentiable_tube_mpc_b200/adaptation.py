@@ -8,7 +8,7 @@ full mode:  reference core/tube_mpc.py:187-249   optional norm clip, vel <- mu v
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import torch

@@ -1,7 +1,6 @@
 """GPU parity on the shapes the slot/tile/segment machinery could get wrong: horizons shorter than the number of commit
 segments, batches that are not whole tiles of 32, a single instance, step-size lists with one entry or with only
 alpha = 0, every kind of obstacle count (none, compile-time instantiated, generic).  Checked against the CPU oracle."""
-from dataclasses import replace
 
 import numpy as np
 import pytest

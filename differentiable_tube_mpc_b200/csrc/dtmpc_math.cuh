@@ -22,6 +22,9 @@
 #ifndef DTMPC_SELECT_MINMAX
 #define DTMPC_SELECT_MINMAX 1
 #endif
+#ifndef DTMPC_FAST_RCP
+#define DTMPC_FAST_RCP 1     // reciprocals by MUFU seed + two Newton steps instead of the IEEE division (see fm::rcp_d)
+#endif
 #ifndef DTMPC_FAST_GUARDS
 #define DTMPC_FAST_GUARDS 1  // exp of a non-positive difference / log of a sum >= 1 without the general-range guards:
                              // -3 % on the final kernels (16.1 -> 15.6 ms per step); it cost +9 % on the first design
@@ -45,6 +48,21 @@ __constant__ double K[12] = {DTMPC_LOG2E, -DTMPC_LN2_HI, -DTMPC_LN2_LO, DTMPC_LN
                              -DTMPC_PIO2_1, -DTMPC_PIO2_2, -DTMPC_PIO2_3, 0x1.8p52, 0x1.6a09e667f3bcdp+0, 0.0};
 enum { LOG2E = 0, NLN2_HI, NLN2_LO, LN2_HI, LN2_LO, TWO_OPI, NPIO2_1, NPIO2_2, NPIO2_3, MAGIC, SQRT2 };
 
+// 1/x from the hardware seed (MUFU.RCP64H: the reciprocal of the upper 32 bits of x) and two Newton steps: relative
+// error 2^-20 -> 2^-40 -> 2^-80, i.e. the correctly rounded reciprocal or its neighbour (<= 1 ulp), in 1 + 4
+// instructions and without the slow-path call of the IEEE division (~14 instructions, a branch and a subroutine per use;
+// profiles/r01g: 3 divisions per line-search step).  Operands on this path are normal numbers (sums >= 1, barrier
+// arguments >= eps, pivots of Q_uu + reg I); 0, subnormals and NaN give inf / NaN, which the non-finite guards report
+// exactly as they report the IEEE results inf / NaN.
+__device__ __forceinline__ double rcp_d(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = ::fma(-x, r, 1.0);
+    r = ::fma(r, e, r);
+    e = ::fma(-x, r, 1.0);
+    return ::fma(r, e, r);
+}
+
 // exp(x) for x <= ~709; x < -700 flushes to 0 (the path only exponentiates z_i - z_max <= 0)
 __device__ __forceinline__ double exp_d(double x) {
     const double t = ::fma(x, K[LOG2E], K[MAGIC]);
@@ -61,8 +79,11 @@ __device__ __forceinline__ double exp_d(double x) {
     return res;
 }
 
-// exp(x) for x <= 0 (differences z_i - z_max of the smooth-min): no overflow guard; NaN propagates
+// exp(x) for x <= 0 (differences z_i - z_max of the smooth-min): no overflow guard.  The argument is clamped at -700:
+// e^-700 = 1e-304 cannot change a sum >= 1 (nor the gradient sums weighted by it) in fp64, which is all the path does
+// with the result.  NaN propagates: arithmetic NaNs are canonical (low word 0), so k = 0 and p = NaN survives.
 __device__ __forceinline__ double exp_nonpos_d(double x) {
+    x = x < -700.0 ? -700.0 : x;
     const double t = ::fma(x, K[LOG2E], K[MAGIC]);
     const int k = __double2loint(t);
     const double kf = t - K[MAGIC];
@@ -71,8 +92,7 @@ __device__ __forceinline__ double exp_nonpos_d(double x) {
     double p = EXP_C[0];
 #pragma unroll
     for (int j = 1; j < DTMPC_EXP_N; ++j) p = ::fma(p, r, EXP_C[j]);
-    const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-    return x < -700.0 ? 0.0 : (x != x ? x : res);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
 // log(s) for s >= 1 finite (s = sum of exp(<= 0) with one term equal to 1); NaN propagates
@@ -83,7 +103,11 @@ __device__ __forceinline__ double log_ge1_d(double s) {
     const bool big = m > K[SQRT2];
     m = big ? m * 0.5 : m;
     e = big ? e + 1 : e;
+#if DTMPC_FAST_RCP
+    const double u = (m - 1.0) * rcp_d(m + 1.0);
+#else
     const double u = (m - 1.0) / (m + 1.0);
+#endif
     const double w = u * u;
     double p = LOG_C[0];
 #pragma unroll
@@ -93,6 +117,26 @@ __device__ __forceinline__ double log_ge1_d(double s) {
     const double ef = (double)e;
     const double res = ::fma(ef, K[LN2_HI], lm) + ef * K[LN2_LO];
     return s != s ? s : res;
+}
+
+// log(s) for 1 <= s <= 2 (the two-term smooth-min: s = 1 + exp(z2 - z1)).  Same operations, hence the same bits, as
+// log_ge1_d on that range, but the exponent is known (0, or 1 after the sqrt(2) fold), so there is no bit surgery and
+// a NaN propagates through the arithmetic by itself.
+__device__ __forceinline__ double log_1to2_d(double s) {
+    const bool big = s > K[SQRT2];
+    const double m = big ? s * 0.5 : s;
+#if DTMPC_FAST_RCP
+    const double u = (m - 1.0) * rcp_d(m + 1.0);
+#else
+    const double u = (m - 1.0) / (m + 1.0);
+#endif
+    const double w = u * u;
+    double p = LOG_C[0];
+#pragma unroll
+    for (int j = 1; j < DTMPC_LOG_N; ++j) p = ::fma(p, w, LOG_C[j]);
+    const double u2 = u + u;
+    const double lm = ::fma(u2 * w, p, u2);
+    return big ? (K[LN2_HI] + lm) + K[LN2_LO] : lm;
 }
 
 // log(s) for positive normal s (the path calls it with s = sum of exp(<= 0) in [1, n_obs])
@@ -150,6 +194,7 @@ template <> struct M<double> {
     static __device__ __forceinline__ double log_(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp_nonpos_(double x) { return ::exp(x); }
     static __device__ __forceinline__ double log_ge1_(double x) { return ::log(x); }
+    static __device__ __forceinline__ double log_1to2_(double x) { return ::log(x); }
     static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { ::sincos(x, s, c); }
 #else
     static __device__ __forceinline__ double exp_(double x) { return fm::exp_d(x); }
@@ -157,13 +202,20 @@ template <> struct M<double> {
 #if DTMPC_FAST_GUARDS
     static __device__ __forceinline__ double exp_nonpos_(double x) { return fm::exp_nonpos_d(x); }
     static __device__ __forceinline__ double log_ge1_(double x) { return fm::log_ge1_d(x); }
+    static __device__ __forceinline__ double log_1to2_(double x) { return fm::log_1to2_d(x); }
 #else
     static __device__ __forceinline__ double exp_nonpos_(double x) { return fm::exp_d(x); }
     static __device__ __forceinline__ double log_ge1_(double x) { return fm::log_d(x); }
+    static __device__ __forceinline__ double log_1to2_(double x) { return fm::log_d(x); }
 #endif
     static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { fm::sincos_d(x, s, c); }
 #endif
     static __device__ __forceinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
+#if DTMPC_FAST_RCP
+    static __device__ __forceinline__ double rcp_(double x) { return fm::rcp_d(x); }
+#else
+    static __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+#endif
     // compare-select (DSETP + 2 FSEL) instead of fmax/fmin (~9 instructions with their NaN rules); a NaN in `a`
     // propagates, which is what torch.clamp / torch.maximum do
 #if DTMPC_SELECT_MINMAX
@@ -183,6 +235,8 @@ template <> struct M<float> {
     static __device__ __forceinline__ float log_(float x) { return ::logf(x); }
     static __device__ __forceinline__ float exp_nonpos_(float x) { return ::expf(x); }
     static __device__ __forceinline__ float log_ge1_(float x) { return ::logf(x); }
+    static __device__ __forceinline__ float log_1to2_(float x) { return ::logf(x); }
+    static __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
     static __device__ __forceinline__ void sincos_(float x, float *s, float *c) { ::sincosf(x, s, c); }
     static __device__ __forceinline__ float atan2_(float y, float x) { return ::atan2f(y, x); }
     static __device__ __forceinline__ float max_(float a, float b) { return a < b ? b : a; }
@@ -220,6 +274,7 @@ template <typename R> struct Theta {
     // a = max(alpha, eps) for the dynamics (eps_dyn) and for the jacobian/gradients (eps_jac)
     R a_dyn, a_jac, jac_off;
     R c1_dyn, c2_dyn, c3_dyn;  // 1/a, 1/a^2, 1/a^3 of the relaxed branch (a = a_dyn)
+    R c2_jac, c3_jac;          // 1/a^2, 1/a^3 with a = a_jac: relaxed branch of B' (barrier_dB_jac)
     // per-OCP numerical settings, kept with the lane so that lanes of one warp may work on
     // different OCPs (nominal / auxiliary) without divergent constant-bank reads
     R eps_dyn, eps_jac;
@@ -241,6 +296,8 @@ __device__ __forceinline__ void load_theta(Theta<R> &t, const R *__restrict__ p,
     t.c1_dyn = R(1) / t.a_dyn;
     t.c2_dyn = R(1) / (t.a_dyn * t.a_dyn);
     t.c3_dyn = R(1) / (t.a_dyn * t.a_dyn * t.a_dyn);
+    t.c2_jac = R(1) / (t.a_jac * t.a_jac);
+    t.c3_jac = R(1) / (t.a_jac * t.a_jac * t.a_jac);
 }
 
 // ---------------------------------------------------------------------------
@@ -371,7 +428,8 @@ __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx
     }
     const R reach = sizeof(R) == 8 ? R(-40) : R(-18);
     R s, sx = R(0), sy = R(0);
-    if (z3 - z1 > reach) {
+    const bool far = z3 - z1 > reach;
+    if (far) {
         s = R(0);
 #pragma unroll 1
         for (int i = 0; i < n; ++i) {
@@ -392,9 +450,9 @@ __device__ __forceinline__ void eval_h(const EnvT<R> &e, R px, R py, R &h, R &gx
             sy = m::fma_(e2, R(2) * ay2, R(2) * ay1);
         }
     }
-    h = e.ninv_beta * (z1 + m::log_ge1_(s));
+    h = e.ninv_beta * (z1 + (far ? m::log_ge1_(s) : m::log_1to2_(s)));
     if (GRAD) {
-        const R inv_s = R(1) / s;
+        const R inv_s = m::rcp_(s);
         gx = sx * inv_s;
         gy = sy * inv_s;
     }
@@ -515,11 +573,11 @@ __device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC]
         }
     }
     const R reach = sizeof(R) == 8 ? R(-40) : R(-18);
-    R s[NC];
+    R lg[NC];
     bool far = false;
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
-        s[q] = R(1) + m::exp_nonpos_(z2[q] - z1[q]);  // exp(-inf) = 0 for a single obstacle
+        lg[q] = m::log_1to2_(R(1) + m::exp_nonpos_(z2[q] - z1[q]));  // exp(-inf) adds nothing for a single obstacle
         far |= (z3[q] - z1[q] > reach);
     }
     if (far) {  // three or more obstacles within reach of one of the points: the reference's full ordered sum (rare)
@@ -533,22 +591,32 @@ __device__ __forceinline__ void eval_h_multi(const EnvT<R> &e, const R (&px)[NC]
                     const R hi = m::fma_(dy, dy, dx * dx) - e.r2[i];
                     acc += m::exp_nonpos_(e.nbeta * hi - z1[q]);
                 }
-                s[q] = acc;
+                lg[q] = m::log_ge1_(acc);
             }
         }
     }
 #pragma unroll
-    for (int q = 0; q < NC; ++q) h[q] = e.ninv_beta * (z1[q] + m::log_ge1_(s[q]));
+    for (int q = 0; q < NC; ++q) h[q] = e.ninv_beta * (z1[q] + lg[q]);
 }
 
 // Relaxed inverse barrier of the dynamics (core/barrier.py:36-59) without a data-dependent branch: the relaxed
 // polynomial 1/a - d/a^2 + d^2/a^3 uses the per-instance reciprocals precomputed in Theta.
 template <typename R> __device__ __forceinline__ R barrier_B_dyn(const Theta<R> &t, R z) {
     using m = M<R>;
-    const R safe = R(1) / m::max_(z, t.eps_dyn);
+    const R safe = m::rcp_(m::max_(z, t.eps_dyn));
     const R d = z - t.a_dyn;
     const R relaxed = m::fma_(d * d, t.c3_dyn, m::fma_(-d, t.c2_dyn, t.c1_dyn));
     return z >= t.a_dyn ? safe : relaxed;
+}
+
+// B' of the jacobian / gradient closures (core/systems/dubins_aug_jac.py:26-40, a = a_jac, eps = eps_jac) without a
+// data-dependent branch: -1/max(z, eps)^2 in the safe set, -1/a^2 + 2 (z - a)/a^3 below it (reciprocals from Theta).
+template <typename R> __device__ __forceinline__ R barrier_dB_jac(const Theta<R> &t, R z) {
+    using m = M<R>;
+    const R zc = m::max_(z, t.eps_jac);
+    const R safe = -m::rcp_(zc * zc);
+    const R relaxed = m::fma_(R(2) * (z - t.a_jac), t.c3_jac, -t.c2_jac);
+    return z >= t.a_jac ? safe : relaxed;
 }
 
 // Augmented state carried along a rollout: (px, py, th, b) plus B(h_bar(x)) of the CURRENT state, which the next
@@ -594,9 +662,6 @@ __device__ __forceinline__ void step_multi(const EnvT<R> &e, const Theta<R> &t, 
     }
 }
 
-// barrier_dB is defined below (jacobian section)
-template <typename R> __device__ __forceinline__ R barrier_dB(R z, R a, R eps);
-
 // step() that also returns g = B'(h_jac(x+)) grad h(x+), the quantity the barrier row of the augmented jacobian is
 // built from (core/systems/dubins_aug_jac.py:95-129).  The state update is bit-identical to step(): h comes out of
 // the same operation sequence in eval_h<R, true> and eval_h_multi.
@@ -612,7 +677,7 @@ __device__ __forceinline__ void step_g(const EnvT<R> &e, const Theta<R> &t, Stat
     R h, hx, hy;
     eval_h<R, true, NOBS>(e, pxn, pyn, h, hx, hy);
     const R Bn = barrier_B_dyn(t, h - t.tight);
-    const R dB = barrier_dB(h - t.jac_off, t.a_jac, t.eps_jac);
+    const R dB = barrier_dB_jac(t, h - t.jac_off);
     gx = dB * hx;
     gy = dB * hy;
     const R bn = m::fma_(-t.gamma, x.Bc - x.b, Bn);
@@ -673,7 +738,7 @@ template <typename R>
 __device__ __forceinline__ void barrier_grad(const EnvT<R> &e, const Theta<R> &t, R px, R py, R &gx, R &gy, R &h) {
     R hx, hy;
     eval_h<R, true>(e, px, py, h, hx, hy);
-    R dB = barrier_dB(h - t.jac_off, t.a_jac, t.eps_jac);
+    R dB = barrier_dB_jac(t, h - t.jac_off);
     gx = dB * hx;
     gy = dB * hy;
 }
@@ -714,9 +779,9 @@ template <typename R> __device__ __forceinline__ void lu2_factor(LU2<R> &f, R q0
     R r00 = f.swap ? q10 : q00, r01 = f.swap ? q11 : q01;
     R r10 = f.swap ? q00 : q10, r11 = f.swap ? q01 : q11;
     f.a01 = r01;
-    f.inv00 = R(1) / r00;
+    f.inv00 = M<R>::rcp_(r00);
     f.l = r10 * f.inv00;
-    f.inv11 = R(1) / M<R>::fma_(-f.l, r01, r11);
+    f.inv11 = M<R>::rcp_(M<R>::fma_(-f.l, r01, r11));
 }
 template <typename R> __device__ __forceinline__ void lu2_solve(const LU2<R> &f, R b0, R b1, R &x0, R &x1) {
     R c0 = f.swap ? b1 : b0, c1 = f.swap ? b0 : b1;

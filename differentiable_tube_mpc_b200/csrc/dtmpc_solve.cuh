@@ -417,12 +417,12 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 #define DTMPC_FWD_STAGES 4
 #endif
 constexpr int XR = 6;
-constexpr int TH_ROWS = 14;
+constexpr int TH_ROWS = 16;
 template <typename R> __device__ __forceinline__ void theta_park(R *s, int lane, const Theta<R> &t) {
     R *v = s + lane;
     v[0 * 32] = t.Q0; v[1 * 32] = t.Q1; v[2 * 32] = t.Q2; v[3 * 32] = t.R0; v[4 * 32] = t.R1; v[5 * 32] = t.qb;
     v[6 * 32] = t.gamma; v[7 * 32] = t.tight; v[8 * 32] = t.a_dyn; v[9 * 32] = t.c1_dyn; v[10 * 32] = t.c2_dyn;
-    v[11 * 32] = t.c3_dyn; v[12 * 32] = t.a_jac; v[13 * 32] = t.jac_off;
+    v[11 * 32] = t.c3_dyn; v[12 * 32] = t.a_jac; v[13 * 32] = t.jac_off; v[14 * 32] = t.c2_jac; v[15 * 32] = t.c3_jac;
 }
 template <typename R> __device__ __forceinline__ void theta_fetch(const R *s, int lane, Theta<R> &t) {
     const volatile R *v = s + lane;  // volatile: re-read every step, never hoisted back into registers
@@ -432,7 +432,7 @@ template <typename R> __device__ __forceinline__ void theta_fetch(const R *s, in
 }
 template <typename R> __device__ __forceinline__ void theta_fetch_jac(const R *s, int lane, Theta<R> &t) {
     const volatile R *v = s + lane;
-    t.a_jac = v[12 * 32]; t.jac_off = v[13 * 32];
+    t.a_jac = v[12 * 32]; t.jac_off = v[13 * 32]; t.c2_jac = v[14 * 32]; t.c3_jac = v[15 * 32];
 }
 constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 

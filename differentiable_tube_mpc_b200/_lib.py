@@ -60,7 +60,7 @@ class SolveIO(C.Structure):
         ("target", C.c_void_p), ("target_stride", C.c_int64), ("Xref", C.c_void_p), ("Uref", C.c_void_p),
         ("X", C.c_void_p), ("V", C.c_void_p), ("K", C.c_void_p), ("kff", C.c_void_p),
         ("iters", C.c_void_p), ("status", C.c_void_p), ("alpha_idx", C.c_void_p),
-        ("costs", C.c_void_p), ("margins", C.c_void_p),
+        ("costs", C.c_void_p), ("margins", C.c_void_p), ("fail_at", C.c_void_p),
     ]
 
 
@@ -76,14 +76,21 @@ class SensIO(C.Structure):
     ]
 
 
+class Disturbance(C.Structure):
+    """struct dtmpc_disturbance"""
+    _fields_ = [("low", C.c_double * 3), ("high", C.c_double * 3), ("seed", C.c_uint64), ("first_instance", C.c_int64),
+                ("step", C.c_void_p)]
+
+
 # every symbol include/dtmpc.h declares (tests/test_abi.py checks the header against this list)
 _PER_DTYPE = ("ilqr_solve", "tube_solve", "tube_step", "sensitivity", "ift_accumulate", "reduce_columns", "rollout", "primitives",
               "plant_step")
 EXPORTS = ["dtmpc_abi_version", "dtmpc_last_error", "dtmpc_kernel_launches", "dtmpc_solve_workspace_bytes", "dtmpc_sens_workspace_bytes", "dtmpc_step_workspace_bytes",
-           "dtmpc_reduce_workspace_bytes", "dtmpc_measure_fp64_peak_tflops", "dtmpc_measure_fp32_peak_tflops"] + [
+           "dtmpc_reduce_workspace_bytes", "dtmpc_measure_fp64_peak_tflops", "dtmpc_measure_fp32_peak_tflops",
+           "dtmpc_math_selftest_f64"] + [
     f"dtmpc_{n}_{s}" for n in _PER_DTYPE for s in ("f64", "f32")]
 
-ABI_VERSION = 2   # include/dtmpc.h DTMPC_ABI_VERSION
+ABI_VERSION = 3   # include/dtmpc.h DTMPC_ABI_VERSION
 _lib = None
 
 
@@ -133,7 +140,10 @@ def load() -> C.CDLL:
         f = getattr(L, f"dtmpc_primitives_{s}")
         f.restype, f.argtypes = C.c_int, [pe, po, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         f = getattr(L, f"dtmpc_plant_step_{s}")
-        f.restype, f.argtypes = C.c_int, [pe, po, po, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
+        f.restype, f.argtypes = C.c_int, [pe, po, po, i64, vp, vp, vp, i64, vp, i64, vp, C.POINTER(Disturbance), vp, vp, vp,
+                                          vp, vp]
+    L.dtmpc_math_selftest_f64.restype = C.c_int
+    L.dtmpc_math_selftest_f64.argtypes = [vp, i64, vp, vp]
     L.dtmpc_measure_fp64_peak_tflops.restype = C.c_double
     L.dtmpc_measure_fp64_peak_tflops.argtypes = [i32, vp]
     L.dtmpc_measure_fp32_peak_tflops.restype = C.c_double

@@ -35,7 +35,8 @@ class TubeMPCFunction(torch.autograd.Function):
                                         Vn_init.detach(), Va_init.detach(), theta_nom.detach(), theta_aux.detach(),
                                         target=target)
         if bool((rn.status != 0).any()):
-            raise FloatingPointError(f"tube MPC solve: non-finite detected in {int((rn.status != 0).sum())} instance(s)")
+            raise FloatingPointError(ops.failure_message("iLQR-nominal", rn) or
+                                     ops.failure_message("iLQR-auxiliary", ra, shift=4) or "tube MPC solve: non-finite detected")
         ctx.problem = p
         ctx.target = target
         ctx.shared = (theta_nom.dim() == 1, theta_aux.dim() == 1)

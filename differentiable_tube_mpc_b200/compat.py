@@ -237,7 +237,7 @@ def ilqr_solve(*, x0: Tensor, V_init: Tensor, cfg: ILQRConfig, f, f_jac=None, ct
     res = ops.ilqr_solve_batched(dyn.system(ctrl), _ocp(cfg, dyn, jac, cost), xb, Vb, theta,
                                  **_cost_refs(cost, B, T, dev, dtype))
     if bool((res.status != 0).any()):
-        raise FloatingPointError(f"{debug_name}: non-finite detected in {int((res.status != 0).sum())} instance(s)")
+        raise FloatingPointError(ops.failure_message(debug_name, res))
     X, V = (res.X[0], res.V[0]) if x0.dim() == 1 else (res.X, res.V)
     return X.to(x0.device), V.to(x0.device)
 

@@ -10,6 +10,11 @@
 #include <cstring>
 #include <mutex>
 
+// 1: line search, selection and commit in one kernel per iteration (fwdc_kernel); 0: the separate fwd / commit kernels
+#ifndef DTMPC_FUSED_COMMIT
+#define DTMPC_FUSED_COMMIT 1
+#endif
+
 #include "dtmpc_math.cuh"
 #include "dtmpc_sens.cuh"
 #include "dtmpc_solve.cuh"
@@ -90,6 +95,7 @@ template <typename R> void convert_io(const dtmpc_solve_io &s, SolveArgs<R> &a) 
     a.X = (R *)s.X; a.V = (R *)s.V; a.K = (R *)s.K; a.kff = (R *)s.kff;
     a.iters = s.iters; a.status = s.status; a.alpha_idx = s.alpha_idx;
     a.costs = (R *)s.costs; a.margins = (R *)s.margins;
+    a.fail_at = s.fail_at;
 }
 
 // ---------------------------------------------------------------------------
@@ -159,7 +165,12 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     for (int c = 0; c < P.ocp.n_alpha; ++c)
         if (P.ocp.alphas[c] != R(0)) P.eval_idx[P.n_eval++] = c;
     for (int c = 0, q = 0; c < P.ocp.n_alpha; ++c) P.eval_pos[c] = P.ocp.alphas[c] != R(0) ? q++ : -1;
+#if DTMPC_FUSED_COMMIT
+    P.n_seg = P.n_eval > 0 ? P.n_eval : 1;   // one horizon segment per candidate warp (fwdc_kernel, phase 3)
+    if (P.n_seg > T) P.n_seg = T;
+#else
     P.n_seg = T < MAX_SEG ? T : MAX_SEG;
+#endif
     P.seg_len = (T + P.n_seg - 1) / P.n_seg;
     P.n_seg = (T + P.seg_len - 1) / P.seg_len;
     // kernels with the obstacle count fixed at compile time (1..8 circles, smooth-min; the reference scenario has 5)
@@ -168,8 +179,38 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     P.parity = 0;
     init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
     const unsigned gFwd = (unsigned)((B + 31) / 32);
+    const unsigned gRic = (unsigned)((B + RIC_BLOCK - 1) / RIC_BLOCK);
+#if DTMPC_FUSED_COMMIT
+    const size_t smem = fwdc_smem_bytes(P.n_eval, P.n_seg, sizeof(R));
+    const dim3 blk(32, P.n_eval > 0 ? P.n_eval : 1);
     for (int it = 0; it < P.ocp.max_iter; ++it) {
-        ric_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+        ric_kernel<R><<<gRic, RIC_BLOCK, 0, st>>>(P);
+#define DTMPC_FWDC_LAUNCH(N, U)                                                                          \
+    {                                                                                                    \
+        static bool big_smem_ok = false;   /* > 48 KB of dynamic shared memory needs the opt-in, once */ \
+        if (smem > 48 * 1024 && !big_smem_ok) {                                                          \
+            cudaFuncSetAttribute(fwdc_kernel<R, N, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+            big_smem_ok = true;                                                                          \
+        }                                                                                                \
+        fwdc_kernel<R, N, U><<<gFwd, blk, smem, st>>>(P);                                                \
+    }
+#define DTMPC_FWDC_CASE(N)                                                \
+    case N:                                                               \
+        if (P.use_ref) DTMPC_FWDC_LAUNCH(N, 1) else DTMPC_FWDC_LAUNCH(N, 0) \
+        break;
+        switch (fixed_nobs) {
+            DTMPC_FWDC_CASE(1) DTMPC_FWDC_CASE(2) DTMPC_FWDC_CASE(3) DTMPC_FWDC_CASE(4)
+            DTMPC_FWDC_CASE(5) DTMPC_FWDC_CASE(6) DTMPC_FWDC_CASE(7) DTMPC_FWDC_CASE(8)
+            default: DTMPC_FWDC_LAUNCH(-1, -1)
+        }
+#undef DTMPC_FWDC_CASE
+#undef DTMPC_FWDC_LAUNCH
+        P.parity ^= 1;
+    }
+    count_launches(1ull + 2ull * (unsigned long long)P.ocp.max_iter);
+#else
+    for (int it = 0; it < P.ocp.max_iter; ++it) {
+        ric_kernel<R><<<gRic, RIC_BLOCK, 0, st>>>(P);
         {
             const int nc = fwd_candidates_per_thread(P.n_eval);
             const int ny = (P.n_eval + nc - 1) / nc;
@@ -202,6 +243,7 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
         P.parity ^= 1;
     }
     count_launches(1ull + 3ull * (unsigned long long)P.ocp.max_iter);
+#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "iLQR kernel launch");
     return DTMPC_OK;
@@ -222,8 +264,10 @@ bool sens_io_ok(const dtmpc_sens_io *s, bool accumulate_only) {
     if ((s->Xref == nullptr) != (s->Uref == nullptr)) return false;
     if (s->Xref && s->xref_row != 3 && s->xref_row != 4) return false;
     if (s->gx_row != 0 && s->gx_row != 3 && s->gx_row != 4) return false;
-    const bool wants_cost_ref = s->g_theta || accumulate_only;
-    if (wants_cost_ref && !s->Xref && !s->target) return false;
+    if (!s->Xref && !s->target) return false;   // both sweeps read the cost reference (also for the deltas alone)
+    for (const void *q : {s->X, s->V, s->Uref, s->gu, s->Xbar, (const void *)s->dX, (const void *)s->dV, (const void *)s->dL,
+                          (const void *)s->gUref})   // state / control rows move as 16-byte vectors
+        if (((uintptr_t)q & 15u) != 0) return false;
     if (!accumulate_only && !s->gx && !s->Xbar) return false;
     return true;
 }
@@ -282,6 +326,7 @@ constexpr int MAX_DEVICES = 64;
 struct ChunkStreams {
     cudaStream_t s[MAX_CHUNKS];
     cudaEvent_t fork, done[MAX_CHUNKS];
+    std::mutex enqueue;   // the events above are shared by every chunked call on this device (f32 and f64 alike)
     bool ready = false;
 };
 ChunkStreams *chunk_streams() {
@@ -334,6 +379,7 @@ template <typename R> void offset_io(SolveArgs<R> &a, long long off, int T, int 
     if (a.alpha_idx) a.alpha_idx += off * max_iter;
     if (a.costs) a.costs += off * max_iter;
     if (a.margins) a.margins += off * max_iter;
+    if (a.fail_at) a.fail_at += off * 2;
 }
 
 template <typename R>
@@ -369,9 +415,8 @@ int solve_impl(const dtmpc_env *env, const dtmpc_ocp *o0, const dtmpc_ocp *o1, l
     if (!cs) n_chunks = 1;
     const long long per = chunk_size(B, n_chunks);
     // the pool's fork/done events are shared by every call on this device: enqueue one chunked call at a time
-    static std::mutex enqueue_mu;
-    std::unique_lock<std::mutex> enqueue_lock(enqueue_mu, std::defer_lock);
-    if (n_chunks > 1) enqueue_lock.lock();
+    std::unique_lock<std::mutex> enqueue_lock;
+    if (n_chunks > 1) enqueue_lock = std::unique_lock<std::mutex>(cs->enqueue);
     if (n_chunks > 1) {
         cudaError_t e = cudaEventRecord(cs->fork, user);
         if (e != cudaSuccess) return cuda_fail(e, "chunk fork");
@@ -434,7 +479,7 @@ int sens_impl(const dtmpc_env *env, const dtmpc_ocp *ocp, long long B, const dtm
     if (!env_ok(env) || !ocp_ok(ocp)) return fail(DTMPC_E_BADARG, "bad env/ocp description");
     if (B < 0) return fail(DTMPC_E_BADARG, "negative batch");
     if (B == 0) return DTMPC_OK;
-    if (!sens_io_ok(io, accumulate_only)) return fail(DTMPC_E_BADARG, "missing buffer in sensitivity io");
+    if (!sens_io_ok(io, accumulate_only)) return fail(DTMPC_E_BADARG, "missing or misaligned (16 bytes) buffer in sensitivity io");
     SensParams<R> P;
     memset(&P, 0, sizeof(P));
     convert_env(*env, P.env);
@@ -604,13 +649,39 @@ __global__ void primitives_kernel(const __grid_constant__ EnvT<R> E, const __gri
     (void)m::abs_(R(0));
 }
 
-// reference core/tube_mpc.py:990-1023
+// Counter-based disturbance generator: Philox4x32-10 (Salmon et al., SC'11) keyed by the seed, counter = (global
+// instance index, closed-loop step, draw).  A draw is a pure function of (seed, instance, step): independent of the
+// batch size, of the sharding across ranks and of CUDA-graph replay (the step counter lives in device memory).
+struct Philox4 { unsigned v[4]; };
+__host__ __device__ inline Philox4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)M0 * c0, p1 = (unsigned long long)M1 * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{{c0, c1, c2, c3}};
+}
+template <typename R> struct RngT {
+    R low[3], high[3];
+    unsigned long long seed;
+    long long first;          // global index of instance 0
+    const long long *step;    // device counter t
+    int enabled;
+};
+__device__ inline double unit_from_bits(unsigned lo, unsigned hi, double) {   // 53 bits, [0, 1)
+    return (double)((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+__device__ inline float unit_from_bits(unsigned lo, unsigned, float) { return (float)(lo >> 8) * 0x1.0p-24f; }   // 24 bits
+
+// reference core/tube_mpc.py:990-1023; disturbance core/systems/dubins.py:57-65 (w = low + (high - low) * U[0,1)^3)
 template <typename R>
 __global__ void plant_step_kernel(const __grid_constant__ EnvT<R> E, const __grid_constant__ OcpT<R> On,
                                   const __grid_constant__ OcpT<R> Oa, long long B, const R *__restrict__ Un,
                                   const R *__restrict__ Ua, const R *__restrict__ theta_n, long long sn,
-                                  const R *__restrict__ theta_a, long long sa, const R *__restrict__ w, R *xh, R *xhb,
-                                  R *Vn_ws, R *Va_ws) {
+                                  const R *__restrict__ theta_a, long long sa, const R *__restrict__ w,
+                                  const __grid_constant__ RngT<R> G, R *xh, R *xhb, R *Vn_ws, R *Va_ws) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int T = On.T;
@@ -625,7 +696,17 @@ __global__ void plant_step_kernel(const __grid_constant__ EnvT<R> E, const __gri
         x.Bc = barrier_of_state(E, ta, x.px, x.py);
         step(E, ta, x, Ua[i * (2LL * T)], Ua[i * (2LL * T) + 1]);
         R w0 = R(0), w1 = R(0), w2 = R(0);
-        if (w) { w0 = w[3 * i]; w1 = w[3 * i + 1]; w2 = w[3 * i + 2]; }
+        if (w) {
+            w0 = w[3 * i]; w1 = w[3 * i + 1]; w2 = w[3 * i + 2];
+        } else if (G.enabled) {
+            const unsigned long long gi = (unsigned long long)(G.first + i), t = (unsigned long long)*G.step;
+            const unsigned k0 = (unsigned)G.seed, k1 = (unsigned)(G.seed >> 32);
+            const Philox4 a = philox4x32_10((unsigned)gi, (unsigned)(gi >> 32), (unsigned)t, 0u, k0, k1);
+            const Philox4 b = philox4x32_10((unsigned)gi, (unsigned)(gi >> 32), (unsigned)t, 1u, k0, k1);
+            w0 = G.low[0] + (G.high[0] - G.low[0]) * unit_from_bits(a.v[0], a.v[1], R(0));
+            w1 = G.low[1] + (G.high[1] - G.low[1]) * unit_from_bits(a.v[2], a.v[3], R(0));
+            w2 = G.low[2] + (G.high[2] - G.low[2]) * unit_from_bits(b.v[0], b.v[1], R(0));
+        }
         xh[4 * i] = x.px + w0; xh[4 * i + 1] = x.py + w1; xh[4 * i + 2] = x.th + w2; xh[4 * i + 3] = x.b;
     }
     {
@@ -642,6 +723,22 @@ __global__ void plant_step_kernel(const __grid_constant__ EnvT<R> E, const __gri
         Va_ws[i * (2LL * T) + 2 * k] = Ua[i * (2LL * T) + 2 * s];
         Va_ws[i * (2LL * T) + 2 * k + 1] = Ua[i * (2LL * T) + 2 * s + 1];
     }
+}
+
+__global__ void math_selftest_kernel(const double *__restrict__ x, long long n, double *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using m = M<double>;
+    const double v = x[i], a = ::fabs(v);
+    double s, c;
+    m::sincos_(v, &s, &c);
+    double *o = out + 6 * i;
+    o[0] = m::exp_nonpos_(-a);
+    o[1] = m::log_ge1_(1.0 + a);
+    o[2] = m::log_1to2_(1.0 + (a - ::floor(a)));
+    o[3] = s;
+    o[4] = c;
+    o[5] = m::rcp_(v);
 }
 
 template <typename R> __global__ void fma_peak_kernel(R *out, int iters) {
@@ -778,8 +875,8 @@ size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size)
     }                                                                                                                 \
     int dtmpc_plant_step_##SUFFIX(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,        \
                                   const void *Un, const void *Ua, const void *theta_n, int64_t sn,                    \
-                                  const void *theta_a, int64_t sa, const void *w, void *xh, void *xhb, void *Vn_ws,   \
-                                  void *Va_ws, void *stream) {                                                        \
+                                  const void *theta_a, int64_t sa, const void *w, const dtmpc_disturbance *rng,       \
+                                  void *xh, void *xhb, void *Vn_ws, void *Va_ws, void *stream) {                      \
         if (!env_ok(env) || !ocp_ok(nom) || !ocp_ok(aux) || B < 0)                                                    \
             return fail(DTMPC_E_BADARG, "bad env/ocp description");                                                   \
         if (B == 0) return DTMPC_OK;                                                                                  \
@@ -790,16 +887,38 @@ size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size)
         convert_env(*env, E);                                                                                         \
         convert_ocp(*nom, On);                                                                                        \
         convert_ocp(*aux, Oa);                                                                                        \
+        RngT<R> G;                                                                                                    \
+        memset(&G, 0, sizeof(G));                                                                                     \
+        if (!w && rng) {                                                                                              \
+            if (!rng->step) return fail(DTMPC_E_BADARG, "disturbance generator without a step counter");              \
+            for (int c = 0; c < 3; ++c) {                                                                             \
+                G.low[c] = (R)rng->low[c];                                                                            \
+                G.high[c] = (R)rng->high[c];                                                                          \
+            }                                                                                                         \
+            G.seed = rng->seed;                                                                                       \
+            G.first = rng->first_instance;                                                                            \
+            G.step = (const long long *)rng->step;                                                                    \
+            G.enabled = 1;                                                                                            \
+        }                                                                                                             \
         count_launches(1);                                                                                            \
         plant_step_kernel<R><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(                          \
             E, On, Oa, B, (const R *)Un, (const R *)Ua, (const R *)theta_n, sn, (const R *)theta_a, sa,               \
-            (const R *)w, (R *)xh, (R *)xhb, (R *)Vn_ws, (R *)Va_ws);                                                 \
+            (const R *)w, G, (R *)xh, (R *)xhb, (R *)Vn_ws, (R *)Va_ws);                                              \
         cudaError_t e = cudaGetLastError();                                                                           \
         return e == cudaSuccess ? DTMPC_OK : cuda_fail(e, "plant step kernel launch");                                \
     }
 
 DTMPC_DEFINE(f64, double)
 DTMPC_DEFINE(f32, float)
+
+int dtmpc_math_selftest_f64(const void *x, int64_t n, void *out, void *stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(DTMPC_E_BADARG, "bad selftest arguments");
+    if (n == 0) return DTMPC_OK;
+    count_launches(1);
+    math_selftest_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const double *)x, n, (double *)out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DTMPC_OK : cuda_fail(e, "selftest kernel launch");
+}
 
 double dtmpc_measure_fp64_peak_tflops(int32_t iters, void *stream) { return peak_impl<double>(iters, stream); }
 double dtmpc_measure_fp32_peak_tflops(int32_t iters, void *stream) { return peak_impl<float>(iters, stream); }

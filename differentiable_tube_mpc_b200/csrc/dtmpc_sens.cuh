@@ -41,10 +41,29 @@ template <typename R> __device__ __forceinline__ R alpha_grad_weight(const Theta
     return t.alpha > t.eps_jac ? R(1) : (t.alpha == t.eps_jac ? R(0.5) : R(0));
 }
 
+// B(z), dB/da (z) of the gradient-time barrier (a = a_jac, eps = eps_jac; core/barrier.py:36-59 and its derivative with
+// respect to a in the relaxed branch) without data-dependent branches or divisions: c1 = 1/a, c4 = 1/a^4 are per-thread
+// constants, 1/a^2 and 1/a^3 come with Theta.
+template <typename R> struct JacConsts { R c1, c4; };
+template <typename R> __device__ __forceinline__ JacConsts<R> jac_consts(const Theta<R> &t) {
+    return JacConsts<R>{M<R>::rcp_(t.a_jac), t.c2_jac * t.c2_jac};
+}
+template <typename R> __device__ __forceinline__ R barrier_B_jac(const Theta<R> &t, const JacConsts<R> &c, R z) {
+    using m = M<R>;
+    const R safe = m::rcp_(m::max_(z, t.eps_jac));
+    const R d = z - t.a_jac;
+    const R relaxed = m::fma_(d * d, t.c3_jac, m::fma_(-d, t.c2_jac, c.c1));
+    return z >= t.a_jac ? safe : relaxed;
+}
+template <typename R> __device__ __forceinline__ R barrier_dB_da_jac(const Theta<R> &t, const JacConsts<R> &c, R z) {
+    const R d = z - t.a_jac;
+    return z >= t.a_jac ? R(0) : (R(-3) * d * d) * c.c4;
+}
+
 template <typename R>
-__device__ __forceinline__ void accumulate_stage(const Theta<R> &t, GradAcc<R> &g, R aw, R px, R py, R pth, R pb, R u0,
-                                                 R u1, R r0, R r1, R r2, R q0, R q1, R dx0, R dx1, R dx2, R dx3, R du0,
-                                                 R du1, R lam_b_next, R h_curr, R h_next) {
+__device__ __forceinline__ void accumulate_stage(const Theta<R> &t, const JacConsts<R> &jc, GradAcc<R> &g, R aw, R px, R py,
+                                                 R pth, R pb, R u0, R u1, R r0, R r1, R r2, R q0, R q1, R dx0, R dx1, R dx2,
+                                                 R dx3, R du0, R du1, R lam_b_next, R h_curr, R h_next) {
     using m = M<R>;
     g.gQ0 = m::fma_(R(2) * (px - r0), dx0, g.gQ0);
     g.gQ1 = m::fma_(R(2) * (py - r1), dx1, g.gQ1);
@@ -54,10 +73,10 @@ __device__ __forceinline__ void accumulate_stage(const Theta<R> &t, GradAcc<R> &
     g.gqb = m::fma_(R(2) * pb, dx3, g.gqb);
     // dynamics term  delta_lambda_{k+1}[b] * b_next(theta)  with  b_next = B(hn) - gamma (B(hc) - b)
     const R hn = h_next - t.tight, hc = h_curr - t.tight;
-    const R Bc = barrier_B(hc, t.a_jac, t.eps_jac);
-    g.ga = m::fma_(lam_b_next, aw * (barrier_dB_da(hn, t.a_jac) - t.gamma * barrier_dB_da(hc, t.a_jac)), g.ga);
+    const R Bc = barrier_B_jac(t, jc, hc);
+    g.ga = m::fma_(lam_b_next, aw * (barrier_dB_da_jac(t, jc, hn) - t.gamma * barrier_dB_da_jac(t, jc, hc)), g.ga);
     g.gg = m::fma_(lam_b_next, -(Bc - pb), g.gg);
-    g.gt = m::fma_(lam_b_next, t.gamma * barrier_dB(hc, t.a_jac, t.eps_jac) - barrier_dB(hn, t.a_jac, t.eps_jac), g.gt);
+    g.gt = m::fma_(lam_b_next, t.gamma * barrier_dB_jac(t, hc) - barrier_dB_jac(t, hn), g.gt);
 }
 
 template <typename R> __device__ __forceinline__ void store_grads(R *out, const GradAcc<R> &g) {
@@ -86,16 +105,24 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     const R *gxp = a.gx ? a.gx + i * ((long long)gxr * (T + 1)) : nullptr;
     const R *gup = a.gu ? a.gu + i * (2LL * T) : nullptr;
     const R *Xb = a.Xbar ? a.Xbar + i * (4LL * (T + 1)) : nullptr;
+    const long long xrow = a.xref_row;
+    const R *xrp = a.Xref ? a.Xref + i * (xrow * (T + 1)) : nullptr;
+    const R *urp = a.Uref ? a.Uref + i * (2LL * T) : nullptr;
+    R *gxo = a.gXref ? a.gXref + i * (3LL * (T + 1)) : nullptr;
+    R *guo = a.gUref ? a.gUref + i * (2LL * T) : nullptr;
     const R gam = th.gamma, dt = E.dt;
+    const JacConsts<R> jc = jac_consts(th);
 
     // upper-level gradient at step k: caller-supplied, or the tracking loss 2(x - xbar), 2b (core/tube_mpc.py:932-944)
     auto upper_gx = [&](int k, R px, R py, R pt, R pb, R &g0, R &g1, R &g2, R &g3) {
         if (gxp) {
             g0 = gxp[gxr * k]; g1 = gxp[gxr * k + 1]; g2 = gxp[gxr * k + 2]; g3 = gxr == 4 ? gxp[4 * k + 3] : R(0);
         } else {
-            g0 = R(2) * (px - Xb[4 * k]);
-            g1 = R(2) * (py - Xb[4 * k + 1]);
-            g2 = R(2) * (pt - Xb[4 * k + 2]);
+            R b0, b1, b2, b3;
+            ld4(Xb + 4 * k, b0, b1, b2, b3);
+            g0 = R(2) * (px - b0);
+            g1 = R(2) * (py - b1);
+            g2 = R(2) * (pt - b2);
             g3 = R(2) * pb;
         }
     };
@@ -106,7 +133,8 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     R gnx, gny;
     R loss_t = R(0), loss_b = R(0);
     {
-        const R px = X[4 * T], py = X[4 * T + 1], pt = X[4 * T + 2], pb = X[4 * T + 3];
+        R px, py, pt, pb;
+        ld4(X + 4 * T, px, py, pt, pb);
         upper_gx(T, px, py, pt, pb, Vx0, Vx1, Vx2, Vx3);
         V00 = R(2) * th.Qf0; V11 = R(2) * th.Qf1; V22 = R(2) * th.Qf2; V33 = R(2) * th.qb;
         V01 = V02 = V03 = V10 = V12 = V13 = V20 = V21 = V23 = V30 = V31 = V32 = R(0);
@@ -118,8 +146,9 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     const R luu0 = R(2) * th.R0, luu1 = R(2) * th.R1;
     const R sreg = R(1e-9);  // core/ddp.py:373
     for (int k = T - 1; k >= 0; --k) {
-        const R px = X[4 * k], py = X[4 * k + 1], pt = X[4 * k + 2], pb = X[4 * k + 3];
-        const R u0 = V[2 * k], u1 = V[2 * k + 1];
+        R px, py, pt, pb, u0, u1;
+        ld4(X + 4 * k, px, py, pt, pb);
+        ld2(V + 2 * k, u0, u1);
         R gcx, gcy, hk;
         barrier_grad(E, th, px, py, gcx, gcy, hk);
         Lin<R> L;
@@ -128,7 +157,8 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         gny = gcy;
         R g0, g1, g2, g3;
         upper_gx(k, px, py, pt, pb, g0, g1, g2, g3);
-        const R gu0 = gup ? gup[2 * k] : R(0), gu1 = gup ? gup[2 * k + 1] : R(0);
+        R gu0 = R(0), gu1 = R(0);
+        if (gup) ld2(gup + 2 * k, gu0, gu1);
 
 #define ROW_M(i)                                                                              \
     const R M##i##0 = m::fma_(V##i##3, L.r0, V##i##0);                                        \
@@ -240,8 +270,9 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         const R K00 = WS(r + 0), K01 = WS(r + 1), K02 = WS(r + 2), K03 = WS(r + 3);
         const R K10 = WS(r + 4), K11 = WS(r + 5), K12 = WS(r + 6), K13 = WS(r + 7);
         const R k0 = WS(r + 8), k1 = WS(r + 9);
-        const R px = X[4 * k], py = X[4 * k + 1], pt = X[4 * k + 2], pb = X[4 * k + 3];
-        const R u0 = V[2 * k], u1 = V[2 * k + 1];
+        R px, py, pt, pb, u0, u1;
+        ld4(X + 4 * k, px, py, pt, pb);
+        ld2(V + 2 * k, u0, u1);
         bool a0, a1;
         active_u(E, u0, u1, a0, a1);
         R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
@@ -253,35 +284,33 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         const R l1 = WS(r + 11) + m::fma_(WS(r + 21), d3, m::fma_(WS(r + 20), d2, m::fma_(WS(r + 19), d1, WS(r + 18) * d0)));
         const R l2 = WS(r + 12) + m::fma_(WS(r + 25), d3, m::fma_(WS(r + 24), d2, m::fma_(WS(r + 23), d1, WS(r + 22) * d0)));
         const R l3 = WS(r + 13) + m::fma_(WS(r + 29), d3, m::fma_(WS(r + 28), d2, m::fma_(WS(r + 27), d1, WS(r + 26) * d0)));
-        dXo[4 * k] = d0; dXo[4 * k + 1] = d1; dXo[4 * k + 2] = d2; dXo[4 * k + 3] = d3;
-        dVo[2 * k] = du0; dVo[2 * k + 1] = du1;
-        dLo[4 * k] = l0; dLo[4 * k + 1] = l1; dLo[4 * k + 2] = l2; dLo[4 * k + 3] = l3;
+        st4(dXo + 4 * k, d0, d1, d2, d3);
+        st2(dVo + 2 * k, du0, du1);
+        st4(dLo + 4 * k, l0, l1, l2, l3);
         bad |= !finite_((l0 + l1) + (l2 + l3) + (du0 + du1));
         const R hk = WS(ROW(k, 0));
         R r0, r1, r2, q0, q1;
-        if (a.Xref) {
-            const R *xr = a.Xref + (i * (T + 1) + k) * a.xref_row;
+        if (xrp) {
+            const R *xr = xrp + k * xrow;
             r0 = xr[0]; r1 = xr[1]; r2 = xr[2];
-            q0 = a.Uref[i * (2LL * T) + 2 * k];
-            q1 = a.Uref[i * (2LL * T) + 2 * k + 1];
+            ld2(urp + 2 * k, q0, q1);
         } else {
             const R *tp = a.target + i * a.target_stride;
             r0 = tp[0]; r1 = tp[1]; r2 = tp[2];
             q0 = R(0); q1 = R(0);
         }
         if (want_g && k > 0)
-            accumulate_stage(th, G, aw, p_px, p_py, p_pt, p_pb, p_u0, p_u1, p_r0, p_r1, p_r2, p_q0, p_q1, p_d0, p_d1, p_d2,
+            accumulate_stage(th, jc, G, aw, p_px, p_py, p_pt, p_pb, p_u0, p_u1, p_r0, p_r1, p_r2, p_q0, p_q1, p_d0, p_d1, p_d2,
                              p_d3, p_du0, p_du1, l3, p_h, hk);
-        if (a.gXref) {
-            R *o = a.gXref + (i * (T + 1) + k) * 3;
+        if (gxo) {
+            R *o = gxo + 3 * k;
             o[0] = -(R(2) * th.Q0) * d0; o[1] = -(R(2) * th.Q1) * d1; o[2] = -(R(2) * th.Q2) * d2;
         }
-        if (a.gUref) {
-            R *o = a.gUref + i * (2LL * T) + 2 * k;
-            o[0] = -(R(2) * th.R0) * du0; o[1] = -(R(2) * th.R1) * du1;
-        }
+        if (guo) st2(guo + 2 * k, -(R(2) * th.R0) * du0, -(R(2) * th.R1) * du1);
         if (a.loss && Xb) {
-            const R e0 = px - Xb[4 * k], e1 = py - Xb[4 * k + 1], e2 = pt - Xb[4 * k + 2];
+            R b0, b1, b2, b3;
+            ld4(Xb + 4 * k, b0, b1, b2, b3);
+            const R e0 = px - b0, e1 = py - b1, e2 = pt - b2;
             loss_t += m::fma_(e2, e2, m::fma_(e1, e1, e0 * e0));
             loss_b = m::fma_(pb, pb, loss_b);
         }
@@ -299,17 +328,18 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     }
     {
         // terminal: delta_lambda_T = g_x,T + phi_xx delta_x_T   (core/ddp.py:425; V_xx,T = diag(2Qf, 2qb))
-        const R px = X[4 * T], py = X[4 * T + 1], pt = X[4 * T + 2], pb = X[4 * T + 3];
+        R px, py, pt, pb;
+        ld4(X + 4 * T, px, py, pt, pb);
         R g0, g1, g2, g3;
         upper_gx(T, px, py, pt, pb, g0, g1, g2, g3);
         const R l0 = m::fma_(R(2) * th.Qf0, d0, g0), l1 = m::fma_(R(2) * th.Qf1, d1, g1);
         const R l2 = m::fma_(R(2) * th.Qf2, d2, g2), l3 = m::fma_(R(2) * th.qb, d3, g3);
-        dXo[4 * T] = d0; dXo[4 * T + 1] = d1; dXo[4 * T + 2] = d2; dXo[4 * T + 3] = d3;
-        dLo[4 * T] = l0; dLo[4 * T + 1] = l1; dLo[4 * T + 2] = l2; dLo[4 * T + 3] = l3;
+        st4(dXo + 4 * T, d0, d1, d2, d3);
+        st4(dLo + 4 * T, l0, l1, l2, l3);
         bad |= !finite_((l0 + l1) + (l2 + l3) + (d0 + d1) + (d2 + d3));
         R r0, r1, r2;
-        if (a.Xref) {
-            const R *xr = a.Xref + (i * (T + 1) + T) * a.xref_row;
+        if (xrp) {
+            const R *xr = xrp + T * xrow;
             r0 = xr[0]; r1 = xr[1]; r2 = xr[2];
         } else {
             const R *tp = a.target + i * a.target_stride;
@@ -317,7 +347,7 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         }
         if (want_g) {
             const R hT = WS(ROW(T, 0));
-            accumulate_stage(th, G, aw, p_px, p_py, p_pt, p_pb, p_u0, p_u1, p_r0, p_r1, p_r2, p_q0, p_q1, p_d0, p_d1, p_d2,
+            accumulate_stage(th, jc, G, aw, p_px, p_py, p_pt, p_pb, p_u0, p_u1, p_r0, p_r1, p_r2, p_q0, p_q1, p_d0, p_d1, p_d2,
                              p_d3, p_du0, p_du1, l3, p_h, hT);
             G.gQf0 = (R(2) * (px - r0)) * d0;
             G.gQf1 = (R(2) * (py - r1)) * d1;
@@ -325,12 +355,14 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
             G.gqb = m::fma_(R(2) * pb, d3, G.gqb);
             store_grads(a.g_theta + i * DTMPC_NTHETA, G);
         }
-        if (a.gXref) {
-            R *o = a.gXref + (i * (T + 1) + T) * 3;
+        if (gxo) {
+            R *o = gxo + 3 * T;
             o[0] = -(R(2) * th.Qf0) * d0; o[1] = -(R(2) * th.Qf1) * d1; o[2] = -(R(2) * th.Qf2) * d2;
         }
         if (a.loss && Xb) {
-            const R e0 = px - Xb[4 * T], e1 = py - Xb[4 * T + 1], e2 = pt - Xb[4 * T + 2];
+            R b0, b1, b2, b3;
+            ld4(Xb + 4 * T, b0, b1, b2, b3);
+            const R e0 = px - b0, e1 = py - b1, e2 = pt - b2;
             loss_t += m::fma_(e2, e2, m::fma_(e1, e1, e0 * e0));
             loss_b = m::fma_(pb, pb, loss_b);
             a.loss[i] = loss_t + loss_b;
@@ -357,6 +389,7 @@ __global__ void __launch_bounds__(SENS_BLOCK) ift_accumulate_kernel(const __grid
     const R *dV = a.dV + i * (2LL * T);
     const R *dL = a.dL + i * (4LL * (T + 1));
     const R aw = alpha_grad_weight(th);
+    const JacConsts<R> jc = jac_consts(th);
     GradAcc<R> G;
     R hc, gx, gy;
     eval_h<R, false>(E, X[0], X[1], hc, gx, gy);
@@ -380,7 +413,7 @@ __global__ void __launch_bounds__(SENS_BLOCK) ift_accumulate_kernel(const __grid
             const R du0 = dV[2 * k], du1 = dV[2 * k + 1];
             R hn;
             eval_h<R, false>(E, X[4 * (k + 1)], X[4 * (k + 1) + 1], hn, gx, gy);
-            accumulate_stage(th, G, aw, px, py, pt, pb, u0, u1, r0, r1, r2, q0, q1, d0, d1, d2, d3, du0, du1,
+            accumulate_stage(th, jc, G, aw, px, py, pt, pb, u0, u1, r0, r1, r2, q0, q1, d0, d1, d2, d3, du0, du1,
                              dL[4 * (k + 1) + 3], hc, hn);
             hc = hn;
             if (a.gXref) {

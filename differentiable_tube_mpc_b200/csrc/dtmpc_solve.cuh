@@ -44,6 +44,7 @@ template <typename R> struct SolveArgs {
     R *X, *V, *K, *kff;
     int *iters, *status, *alpha_idx;
     R *costs, *margins;
+    int *fail_at;
 };
 
 template <typename R> struct SolveWs {
@@ -208,6 +209,10 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     P.ws.flags[i] = 0;
     P.ws.list[0][i] = (int)i;
     if (P.status_shift == 0) P.io.status[i] = 0;
+    if (P.io.fail_at) {
+        P.io.fail_at[2 * i] = -1;
+        P.io.fail_at[2 * i + 1] = -1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -222,11 +227,31 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
 #ifndef DTMPC_RIC_PREFETCH
 #define DTMPC_RIC_PREFETCH 0
 #endif
+// DTMPC_RIC_ASYNC = 1 fetches the inputs of step k-2 with cp.async (LDGSTS: global -> shared without a register in
+// between) into a thread-private ring of RIC_STAGES buffers while step k is computed (every thread reads only what it
+// copied itself, so cp.async.wait_group is the only synchronisation).  Measured on B200 (profiles/r02c, B = 65,536):
+// the sweep alone gains 4 % (126.9 -> 121.7 us, +9 % instructions), but its 27 KB of shared memory per CTA comes out
+// of the L1 the concurrently running line search lives on: the step went from 14.6 to 16.9 ms.  Off.
+#ifndef DTMPC_RIC_ASYNC
+#define DTMPC_RIC_ASYNC 0
+#endif
+#ifndef DTMPC_RIC_BLOCK
+#define DTMPC_RIC_BLOCK 64
+#endif
+constexpr int RIC_BLOCK = DTMPC_RIC_BLOCK;
+constexpr int RIC_STAGES = 4, RIC_AHEAD = 2, RIC_ROWS = 13;
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem)), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename R>
 __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
-    const int j = blockIdx.x * LS_BLOCK + threadIdx.x;
+    const int j = blockIdx.x * RIC_BLOCK + threadIdx.x;
+    if (j == 0) P.ws.counts[P.parity ^ 1] = 0;   // fwdc_kernel of this iteration counts the survivors into it
     if (j >= n_act) return;
     const long long i = P.ws.list[P.parity][j];
     const EnvT<R> &E = P.env;
@@ -266,6 +291,36 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         RefPt<R> r;
         R gx, gy;
     };
+#if DTMPC_RIC_ASYNC
+    __shared__ R sIn[RIC_STAGES][RIC_ROWS][RIC_BLOCK];
+    const bool with_ref = P.use_ref != 0;
+    auto issue = [&](int k, int slot) {   // always commits a group (possibly empty): the group count tracks the steps
+        if (k >= 0) {
+            const R *xk = X + EL(k, TR, 0);
+#pragma unroll
+            for (int r = 0; r < TR; ++r) cp_async_elem<sizeof(R)>(&sIn[slot][r][threadIdx.x], xk + r * 32);
+            if (with_ref) {
+                const R *rk = ref_i + EL(k, RR, 0);
+#pragma unroll
+                for (int r = 0; r < RR; ++r) cp_async_elem<sizeof(R)>(&sIn[slot][TR + r][threadIdx.x], rk + r * 32);
+            }
+        }
+        cp_async_commit();
+    };
+    auto load_step = [&](int slot, RicIn &q) {
+        q.px = sIn[slot][0][threadIdx.x]; q.py = sIn[slot][1][threadIdx.x]; q.pt = sIn[slot][2][threadIdx.x];
+        q.pb = sIn[slot][3][threadIdx.x]; q.u0 = sIn[slot][4][threadIdx.x]; q.u1 = sIn[slot][5][threadIdx.x];
+        q.gx = sIn[slot][6][threadIdx.x]; q.gy = sIn[slot][7][threadIdx.x];
+        if (with_ref) {
+            q.r.x0 = sIn[slot][8][threadIdx.x]; q.r.x1 = sIn[slot][9][threadIdx.x]; q.r.x2 = sIn[slot][10][threadIdx.x];
+            q.r.u0 = sIn[slot][11][threadIdx.x]; q.r.u1 = sIn[slot][12][threadIdx.x];
+        } else {
+            q.r.x0 = t0; q.r.x1 = t1; q.r.x2 = t2; q.r.u0 = R(0); q.r.u1 = R(0);
+        }
+    };
+#pragma unroll
+    for (int a = 0; a < RIC_AHEAD; ++a) issue(T - 1 - a, a);
+#else
     auto load_step = [&](int k, RicIn &q) {
         const R *xk = X + EL(k, TR, 0);
         q.px = xk[0 * 32]; q.py = xk[1 * 32]; q.pt = xk[2 * 32]; q.pb = xk[3 * 32];
@@ -273,14 +328,26 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         ref_at(P, ref_i + EL(k, RR, 0), true, t0, t1, t2, q.r);
         q.gx = xk[6 * 32]; q.gy = xk[7 * 32];
     };
+#endif
     R gnx = X[EL(T, TR, 6)], gny = X[EL(T, TR, 7)];  // g at x_T, then carried backwards
     RicIn in;
-#if DTMPC_RIC_PREFETCH
+#if DTMPC_RIC_PREFETCH && !DTMPC_RIC_ASYNC
     load_step(T - 1, in);
+#endif
+    int bad_k = -1;   // horizon index at which the backward sweep first produced a non-finite feed-forward gain
+#if DTMPC_RIC_ASYNC
+    int slot = 0;
 #endif
     for (int k = T - 1; k >= 0; --k) {
         RicIn nx;
-#if DTMPC_RIC_PREFETCH
+#if DTMPC_RIC_ASYNC
+        // the buffer refilled here was read RIC_STAGES - RIC_AHEAD = 2 steps ago
+        issue(k - RIC_AHEAD, (slot + RIC_AHEAD) & (RIC_STAGES - 1));
+        cp_async_wait<RIC_AHEAD>();
+        load_step(slot, in);
+        slot = (slot + 1) & (RIC_STAGES - 1);
+        nx = in;
+#elif DTMPC_RIC_PREFETCH
         load_step(k > 0 ? k - 1 : 0, nx);
 #else
         load_step(k, in);
@@ -357,6 +424,7 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
             o[8 * 32] = k0;
             o[9 * 32] = k1;
         }
+        if (bad_k < 0 && !finite_(k0 + k1)) bad_k = k;   // the sweep runs backwards: the first hit is where it broke
         // V_x = Q_x + K^T Q_uu k + K^T Q_u + Q_xu k   (un-regularised Q_uu, core/ddp.py:251)
         const R s0 = m::fma_(Quu01, k1, Quu00 * k0) + Qu0;
         const R s1 = m::fma_(Quu11, k1, Quu10 * k0) + Qu1;
@@ -382,7 +450,13 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     // own step, so a NaN or Inf produced anywhere is still there at k = 0.
     const R chk = (Vx0 + Vx1) + (Vx2 + Vx3) + (V00 + V11) + (V22 + V33) + (V01 + V02) + (V03 + V12) + (V13 + V23) +
                   (V10 + V20) + (V30 + V21) + (V31 + V32);
-    if (!finite_(chk)) P.ws.flags[i] |= 1;
+    if (!finite_(chk)) {
+        P.ws.flags[i] |= 1;
+        if (P.io.fail_at && P.io.fail_at[2 * i] < 0) {
+            P.io.fail_at[2 * i] = P.ws.it[i];
+            P.io.fail_at[2 * i + 1] = bad_k;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -617,6 +691,10 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
             done = conv || it >= o.max_iter;
         } else {
             P.io.status[i] |= DTMPC_ST_NONFINITE << P.status_shift;
+            if (P.io.fail_at && P.io.fail_at[2 * i] < 0) {   // a cost was non-finite (the backward pass reports itself)
+                P.io.fail_at[2 * i] = it;
+                P.io.fail_at[2 * i + 1] = -1;
+            }
         }
         keep = !done;
         P.ws.dec[j] = best_c | (keep ? DEC_KEEP : 0) | (bad ? DEC_BAD : 0);
@@ -641,15 +719,6 @@ __global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const 
 #ifndef DTMPC_SEL_SMEM_THETA
 #define DTMPC_SEL_SMEM_THETA 0  // measured neutral for the commit sweep (18.22 vs 18.21 ms)
 #endif
-__device__ __forceinline__ void st4(double *p, double a, double b, double c, double d) {
-    reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
-}
-__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
-    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
-}
-__device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
-__device__ __forceinline__ void st2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
 
 template <typename R, int NOBS = -1>
 __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_constant__ SolveParams<R> P) {
@@ -784,5 +853,256 @@ __global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_consta
         X0 = N0; X1 = N1; X2 = N2; X3 = N3;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Line search + selection + commit in ONE kernel (round 2).  blockDim = (32, n_eval): a CTA owns 32 slots.
+//   phase 1  every warp rolls out one candidate (as fwd_kernel) and leaves its state at the segment boundaries in
+//            SHARED memory (n_eval x (n_seg - 1) x 5 rows x 32 lanes);
+//   phase 2  warp 0 takes the decision for its 32 slots and reserves the survivors' slots of the next iteration with
+//            ONE atomicAdd per CTA on the slot counter (the survivors of a CTA stay contiguous and in order; CTAs land
+//            in the order they finish.  Results do not depend on which slot an instance occupies: every instance is
+//            computed by the same instruction sequence, tests/test_gpu_graph.py);
+//   phase 3  the warps re-roll the winner, one horizon segment each, from the checkpoints (bit-identical to the
+//            candidate, dtmpc_math.cuh) and write the next trajectory -- or, for an instance that stops, the caller's
+//            result tensors.  The gains and the old trajectory were read by this CTA a moment ago (L1 / L2).
+// Against the separate fwd / commit kernels this drops one launch per iteration, the global checkpoint, decision and
+// ballot arrays with their traffic, the O(#CTAs) rank scan in every commit CTA, and the latency-bound commit launch
+// (a third of the issue efficiency of the line search, profiles/r02a): the commit work now runs at the occupancy of
+// the line search.  The number of segments is the number of candidate warps.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FWDC_MAX_SEG = DTMPC_MAX_ALPHAS;
+
+template <typename R, int NOBS = -1, int UR = -1>
+__global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant__ SolveParams<R> P) {
+    using m = M<R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *sJ = reinterpret_cast<R *>(smem_raw);                 // [MAX_ALPHAS][32] candidate costs
+    R *sTh = sJ + DTMPC_MAX_ALPHAS * 32;                     // [TH_ROWS][32] parked parameters
+    R *sCk = sTh + TH_ROWS * 32;                             // [n_eval][n_seg - 1][CR][32] checkpoints
+    __shared__ int sDec[32], sJn[32];
+    const int n_act = P.ws.counts[P.parity];
+    if ((int)blockIdx.x * 32 >= n_act) return;  // whole CTA
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const bool live = (int)blockIdx.x * 32 + lane < n_act;
+    const int j = live ? blockIdx.x * 32 + lane : n_act - 1;  // idle lanes shadow the last slot (they reach the barriers)
+    const long long i = P.ws.list[P.parity][j];
+    const EnvT<R> &E = P.env;
+    const int T = P.ocp.T;
+    const int n_seg = P.n_seg, seg_len = P.seg_len;
+    const bool valid = wy < P.n_eval;
+    const int a_idx = P.eval_idx[valid ? wy : (P.n_eval > 0 ? P.n_eval - 1 : 0)];
+    const R al = P.ocp.alphas[a_idx];
+    R t0 = R(0), t1 = R(0), t2 = R(0);
+    if (UR < 0 ? !P.use_ref : UR == 0) {
+        const R *tp = P.io.target + i * P.io.target_stride;
+        t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
+    }
+    const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
+    const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
+    const R *ref_i = P.ws.ref + tile_off(i, ref_rows(T));
+    {
+        Theta<R> th;
+        load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
+        if (wy == 0) theta_park(sTh, lane, th);
+    }
+    __syncthreads();
+
+    // ---- phase 1: candidate rollout, cost only -------------------------------------------------------------------
+    State<R> x{X[EL(0, TR, 0)], X[EL(0, TR, 1)], X[EL(0, TR, 2)], X[EL(0, TR, 3)], P.ws.B0[i]};
+    R J = R(0);
+    {
+        int k_ck = seg_len, seg = 0;
+        const R *xp = X, *gp = GK, *rp = ref_i;
+        for (int k = 0; k < T; ++k) {
+            if (k == k_ck) {  // phase 3 restarts the winner from here (uniform branch)
+                R *c = sCk + ((wy * (n_seg - 1) + seg) * CR) * 32 + lane;
+                c[0 * 32] = x.px; c[1 * 32] = x.py; c[2 * 32] = x.th; c[3 * 32] = x.b; c[4 * 32] = x.Bc;
+                k_ck += seg_len;
+                ++seg;
+            }
+            const R X0 = xp[0 * 32], X1 = xp[1 * 32], X2 = xp[2 * 32], X3 = xp[3 * 32];
+            const R v0 = xp[4 * 32], v1 = xp[5 * 32];
+            const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
+            const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
+            const R k0 = gp[8 * 32], k1 = gp[9 * 32];
+            RefPt<R> r;
+            ref_at<R, UR>(P, rp, true, t0, t1, t2, r);
+            xp += TR * 32;
+            gp += GR * 32;
+            rp += RR * 32;
+            Theta<R> tk;
+            tk.eps_dyn = P.ocp.eps_dyn; tk.angle_wrap = P.ocp.angle_wrap;
+            theta_fetch(sTh, lane, tk);
+            // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
+            const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
+            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
+            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
+            R u0 = m::fma_(al, du0, v0), u1 = m::fma_(al, du1, v1);
+            clamp_u(E, u0, u1);
+            J += stage_cost(tk, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
+            State<R> xs[1] = {x};
+            const R a0[1] = {u0}, a1[1] = {u1};
+            step_multi<R, 1, NOBS>(E, tk, xs, a0, a1);
+            x = xs[0];
+        }
+        RefPt<R> r;
+        ref_at<R, UR>(P, rp, false, t0, t1, t2, r);
+        Theta<R> tk;   // the terminal weights are used once: reloaded here instead of held across the sweep
+        tk.angle_wrap = P.ocp.angle_wrap;
+        const R *p = P.io.theta + i * P.io.theta_stride;
+        tk.Qf0 = p[5]; tk.Qf1 = p[6]; tk.Qf2 = p[7]; tk.qb = p[8];
+        J += terminal_cost(tk, x.px, x.py, x.th, x.b, r.x0, r.x1, r.x2);
+        if (valid) sJ[a_idx * 32 + lane] = J;
+    }
+    __syncthreads();
+
+    // ---- phase 2: selection (strict '<' in list order, tolerance break on the accepted costs; core/ddp.py:293-305)
+    if (wy == 0) {
+        bool keep = false;
+        int dec = 0;
+        if (live) {
+            const OcpT<R> &o = P.ocp;
+            const R Jc = P.ws.Jcur[i];
+            bool bad = (P.ws.flags[i] & 1) != 0;
+            int best_c = -1;
+            R best = R(0), second = m::inf_();
+            for (int c = 0; c < o.n_alpha; ++c) {
+                const R v = (o.alphas[c] == R(0)) ? Jc : sJ[c * 32 + lane];
+                bad |= !finite_(v);
+                if (best_c < 0 || v < best) {
+                    if (best_c >= 0) second = m::min_(second, best);
+                    best = v;
+                    best_c = c;
+                } else {
+                    second = m::min_(second, v);
+                }
+            }
+            int it = P.ws.it[i];
+            bool done = true;
+            if (!bad) {
+                if (o.alphas[best_c] != R(0)) P.ws.Jcur[i] = best;
+                if (P.io.alpha_idx) P.io.alpha_idx[i * o.max_iter + it] = best_c;
+                if (P.io.costs) P.io.costs[i * o.max_iter + it] = best;
+                if (P.io.margins) P.io.margins[i * o.max_iter + it] = second - best;
+                const bool conv = it > 0 && (m::abs_(P.ws.prev[i] - best) < o.tol);
+                P.ws.prev[i] = best;
+                ++it;
+                P.ws.it[i] = it;
+                done = conv || it >= o.max_iter;
+            } else {
+                P.io.status[i] |= DTMPC_ST_NONFINITE << P.status_shift;
+                if (P.io.fail_at && P.io.fail_at[2 * i] < 0) {   // a cost was non-finite (the backward pass reports itself)
+                    P.io.fail_at[2 * i] = it;
+                    P.io.fail_at[2 * i + 1] = -1;
+                }
+            }
+            keep = !done;
+            dec = best_c | (keep ? DEC_KEEP : 0) | (bad ? DEC_BAD : 0);
+            if (!keep && P.io.iters) P.io.iters[i] = it;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if (lane == 0 && mask) base = atomicAdd(&P.ws.counts[P.parity ^ 1], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int jn = base + __popc(mask & ((1u << lane) - 1u));
+        if (keep) P.ws.list[P.parity ^ 1][jn] = (int)i;
+        sDec[lane] = dec;
+        sJn[lane] = jn;
+    }
+    __syncthreads();
+    if (!live || wy >= n_seg) return;
+
+    // ---- phase 3: commit the winner, one horizon segment per warp ------------------------------------------------
+    const int seg = wy;
+    const int d = sDec[lane];
+    const bool keep = (d & DEC_KEEP) != 0;
+    const long long jn = sJn[lane];
+    const R alw = (d & DEC_BAD) ? R(0) : P.ocp.alphas[d & 0xff];
+    const bool copy = alw == R(0);  // the current trajectory stays
+    const int k_lo = seg * seg_len, k_hi = min(T, k_lo + seg_len);
+    R *Xn = P.ws.traj[P.parity ^ 1] + tile_off(jn, traj_rows(T));
+    R X0 = X[EL(k_lo, TR, 0)], X1 = X[EL(k_lo, TR, 1)], X2 = X[EL(k_lo, TR, 2)], X3 = X[EL(k_lo, TR, 3)];
+    State<R> xw{X0, X1, X2, X3, R(0)};
+    if (seg == 0) {
+        xw.Bc = P.ws.B0[i];
+        if (keep) {
+            Xn[EL(0, TR, 0)] = X0; Xn[EL(0, TR, 1)] = X1; Xn[EL(0, TR, 2)] = X2; Xn[EL(0, TR, 3)] = X3;
+            Xn[EL(0, TR, 6)] = X[EL(0, TR, 6)]; Xn[EL(0, TR, 7)] = X[EL(0, TR, 7)];
+        } else {
+            st4(P.io.X + i * (4LL * (T + 1)), X0, X1, X2, X3);
+            if (P.write_ref) {
+                R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
+                Ro[EL(0, RR, 0)] = X0; Ro[EL(0, RR, 1)] = X1; Ro[EL(0, RR, 2)] = X2;
+            }
+        }
+    } else if (!copy) {
+        const R *c = sCk + ((P.eval_pos[d & 0xff] * (n_seg - 1) + (seg - 1)) * CR) * 32 + lane;
+        xw.px = c[0 * 32]; xw.py = c[1 * 32]; xw.th = c[2 * 32]; xw.b = c[3 * 32]; xw.Bc = c[4 * 32];
+    }
+    const R *xp = X + EL(k_lo, TR, 0), *gp = GK + EL(k_lo, GR, 0);
+    R *xn = Xn + EL(k_lo, TR, 0);
+    for (int k = k_lo; k < k_hi; ++k) {
+        const R v0 = xp[4 * 32], v1 = xp[5 * 32];
+        const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
+        const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
+        const R k0 = gp[8 * 32], k1 = gp[9 * 32];
+        const R N0 = xp[(TR + 0) * 32], N1 = xp[(TR + 1) * 32];
+        const R N2 = xp[(TR + 2) * 32], N3 = xp[(TR + 3) * 32];
+        R u0 = v0, u1 = v1, gx, gy;
+        if (!copy) {
+            Theta<R> tk;
+            tk.eps_dyn = P.ocp.eps_dyn; tk.eps_jac = P.ocp.eps_jac; tk.angle_wrap = P.ocp.angle_wrap;
+            theta_fetch(sTh, lane, tk);
+            theta_fetch_jac(sTh, lane, tk);
+            const R d0 = xw.px - X0, d1 = xw.py - X1, d2 = xw.th - X2, d3 = xw.b - X3;
+            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
+            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
+            u0 = m::fma_(alw, du0, v0);
+            u1 = m::fma_(alw, du1, v1);
+            clamp_u(E, u0, u1);
+            step_g<R, NOBS>(E, tk, xw, u0, u1, gx, gy);
+        } else {
+            xw.px = N0; xw.py = N1; xw.th = N2; xw.b = N3;
+            gx = xp[(TR + 6) * 32];
+            gy = xp[(TR + 7) * 32];
+        }
+        xp += TR * 32;
+        gp += GR * 32;
+        if (keep) {
+            xn[4 * 32] = u0;
+            xn[5 * 32] = u1;
+            xn[(TR + 0) * 32] = xw.px;
+            xn[(TR + 1) * 32] = xw.py;
+            xn[(TR + 2) * 32] = xw.th;
+            xn[(TR + 3) * 32] = xw.b;
+            xn[(TR + 6) * 32] = gx;
+            xn[(TR + 7) * 32] = gy;
+            xn += TR * 32;
+        } else {
+            st2(P.io.V + i * (2LL * T) + 2 * k, u0, u1);
+            st4(P.io.X + i * (4LL * (T + 1)) + 4 * (k + 1), xw.px, xw.py, xw.th, xw.b);
+            if (P.io.K) {
+                R *Ko = P.io.K + i * (8LL * T) + 8 * k;
+                st4(Ko, K00, K01, K02, K03);
+                st4(Ko + 4, K10, K11, K12, K13);
+            }
+            if (P.io.kff) st2(P.io.kff + i * (2LL * T) + 2 * k, k0, k1);
+            if (P.write_ref) {
+                R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
+                Ro[EL(k + 1, RR, 0)] = xw.px;
+                Ro[EL(k + 1, RR, 1)] = xw.py;
+                Ro[EL(k + 1, RR, 2)] = xw.th;
+                Ro[EL(k, RR, 3)] = u0;
+                Ro[EL(k, RR, 4)] = u1;
+            }
+        }
+        X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+    }
+}
+__host__ inline size_t fwdc_smem_bytes(int n_eval, int n_seg, size_t elem) {
+    const int ne = n_eval > 0 ? n_eval : 1;
+    return elem * 32 * (size_t)(DTMPC_MAX_ALPHAS + TH_ROWS + ne * (n_seg > 1 ? n_seg - 1 : 0) * CR);
+}
+
 
 }  // namespace dtmpc

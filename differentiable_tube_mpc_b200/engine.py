@@ -242,19 +242,42 @@ class DoubleBufferedSteps:
         return out
 
 
+def sum_over_ranks(vec: Tensor, group=None) -> Tensor:
+    """Sum of a small vector over the data-parallel ranks with a FIXED order of additions: the ranks' vectors are
+    all-gathered (one collective, < 2 KB) and added in rank order on every rank.  The result is bitwise the same on
+    all ranks and does not depend on the algorithm NCCL would pick for an all-reduce (ring, tree, NVLS), so runs are
+    reproducible across topologies.  Returns `vec` itself without an initialised process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return vec
+    world = dist.get_world_size(group)
+    src = vec.contiguous()
+    if src.is_cuda and dist.get_backend(group) == "gloo":   # test set-up (several ranks on one GPU): stage through the host
+        src = src.cpu()
+    parts = [torch.empty_like(src) for _ in range(world)]
+    dist.all_gather(parts, src, group=group)
+    total = parts[0].clone()
+    for r in range(1, world):
+        total += parts[r]
+    return total.to(vec.device)
+
+
 def allreduce_shared(step: TubeStep, group=None) -> TubeStep:
     """Sum the batch-summed gradients (and the loss) over the data-parallel ranks: the one collective of the path
-    (Algorithm 2 with shared theta; < 200 bytes, latency bound).  No-op without an initialised process group."""
+    (Algorithm 2 with shared theta; < 200 bytes, latency bound).  The sums are overwritten IN PLACE: a graphed step
+    returns the same static tensors on every replay, so rebinding the fields would detach the caller from them.
+    No-op without an initialised process group."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return step
+    n_aux = step.g_aux_sum.numel()
+    parts = [step.g_aux_sum] + ([step.g_nom_sum] if step.g_nom_sum is not None else [])
+    total = sum_over_ranks(torch.cat(parts), group=group)
+    step.g_aux_sum.copy_(total[:n_aux])
     if step.g_nom_sum is not None:
-        buf = torch.cat([step.g_aux_sum, step.g_nom_sum])
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-        step.g_aux_sum, step.g_nom_sum = buf[:13].clone(), buf[13:].clone()
-    else:
-        dist.all_reduce(step.g_aux_sum, op=dist.ReduceOp.SUM, group=group)
+        step.g_nom_sum.copy_(total[n_aux:])
     return step
 
 

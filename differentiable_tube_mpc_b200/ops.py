@@ -114,13 +114,29 @@ class SolveResult:
     alpha_idx: Optional[Tensor] = None  # [B,max_iter] int32, -1 beyond iters
     costs: Optional[Tensor] = None      # [B,max_iter], nan beyond iters
     margins: Optional[Tensor] = None    # [B,max_iter]
+    fail_at: Optional[Tensor] = None    # [B,2] int32 (iteration, step) of the first non-finite value, (-1,-1) if clean
+
+
+def failure_message(name: str, res: "SolveResult", shift: int = 0) -> Optional[str]:
+    """What the reference prints before it raises (core/ddp.py:138-159 `[NUMERIC-FAIL] name: ... non-finite at ...`):
+    the first failing instance with the iteration / horizon step where the first non-finite value appeared."""
+    bad = ((res.status >> shift) & 15) != 0
+    if not bool(bad.any()):
+        return None
+    i = int(torch.nonzero(bad)[0])
+    where = ""
+    if res.fail_at is not None:
+        it, k = (int(v) for v in res.fail_at[i].tolist())
+        where = f" at (it={it}, k={k})" if k >= 0 else f" at it={it} (line-search / rollout cost)"
+    return f"[NUMERIC-FAIL] {name}: non-finite detected{where} in instance {i} ({int(bad.sum())} of {bad.numel()} failed)"
 
 
 def _alloc_solve(B, T, max_iter, dtype, device, gains, trace, status=None):
     out = dict(
         X=torch.empty(B, T + 1, 4, dtype=dtype, device=device), V=torch.empty(B, T, 2, dtype=dtype, device=device),
         iters=torch.zeros(B, dtype=torch.int32, device=device),
-        status=torch.zeros(B, dtype=torch.int32, device=device) if status is None else status)
+        status=torch.zeros(B, dtype=torch.int32, device=device) if status is None else status,
+        fail_at=torch.empty(B, 2, dtype=torch.int32, device=device))
     if gains:
         out["K"] = torch.zeros(B, T, 2, 4, dtype=dtype, device=device)
         out["k"] = torch.zeros(B, T, 2, dtype=dtype, device=device)
@@ -136,7 +152,7 @@ def _fill_io(io: _lib.SolveIO, x0, V_init, theta, ts, target, gs, Xref, Uref, ou
     io.target, io.target_stride, io.Xref, io.Uref = _ptr(target), gs, _ptr(Xref), _ptr(Uref)
     io.X, io.V, io.K, io.kff = _ptr(out["X"]), _ptr(out["V"]), _ptr(out.get("K")), _ptr(out.get("k"))
     io.iters, io.status, io.alpha_idx = _ptr(out["iters"]), _ptr(out["status"]), _ptr(out.get("alpha_idx"))
-    io.costs, io.margins = _ptr(out.get("costs")), _ptr(out.get("margins"))
+    io.costs, io.margins, io.fail_at = _ptr(out.get("costs")), _ptr(out.get("margins")), _ptr(out.get("fail_at"))
 
 
 def ilqr_solve_batched(system: SystemSpec, ocp: OcpSpec, x0: Tensor, V_init: Tensor, theta: Tensor, *,
@@ -461,11 +477,24 @@ def primitives_batched(system: SystemSpec, ocp: OcpSpec, xh: Tensor, u: Tensor, 
     return out
 
 
+@dataclass
+class DisturbanceSpec:
+    """In-kernel disturbance w = low + (high - low) U[0,1)^3 (core/systems/dubins.py:57-65), Philox4x32-10 keyed by
+    `seed` with counter (first_instance + i, step[0]): `step` is a device int64 tensor of one element, read at kernel
+    run time (so a captured step can be replayed with a moving counter)."""
+    low: Tuple[float, float, float]
+    high: Tuple[float, float, float]
+    seed: int
+    step: Tensor
+    first_instance: int = 0
+
+
 def plant_step_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec, Un: Tensor, Ua: Tensor,
                        theta_nom: Tensor, theta_aux: Tensor, w: Optional[Tensor], xh: Tensor, xh_bar: Tensor,
-                       Vn_ws: Tensor, Va_ws: Tensor) -> None:
-    """In-place closed-loop step (core/tube_mpc.py:990-1023): plant + disturbance, DBaS propagation of the
-    undisturbed successor, nominal propagation, warm-start shift."""
+                       Vn_ws: Tensor, Va_ws: Tensor, rng: Optional[DisturbanceSpec] = None) -> None:
+    """In-place closed-loop step (core/tube_mpc.py:990-1023): plant + disturbance (the tensor `w` [B,3], or drawn in
+    the kernel from `rng`, or none), DBaS propagation of the undisturbed successor, nominal propagation, warm-start
+    shift."""
     L = _lib.load()
     dtype, device = xh.dtype, xh.device
     sfx = _suffix(dtype)
@@ -480,11 +509,31 @@ def plant_step_batched(system: SystemSpec, nominal: OcpSpec, auxiliary: OcpSpec,
     if w is not None:
         w = _chk(w, (B, 3), dtype, "w")
     env_c, n_c, a_c = system.to_c(), nominal.to_c(), auxiliary.to_c()
+    rng_c = None
+    if w is None and rng is not None:
+        if rng.step.device != device or rng.step.dtype != torch.int64 or rng.step.numel() != 1:
+            raise ValueError("rng.step must be a one-element int64 tensor on the compute device")
+        rng_c = _lib.Disturbance()
+        for c in range(3):
+            rng_c.low[c], rng_c.high[c] = float(rng.low[c]), float(rng.high[c])
+        rng_c.seed, rng_c.first_instance, rng_c.step = int(rng.seed) & (2 ** 64 - 1), int(rng.first_instance), rng.step.data_ptr()
     with torch.cuda.device(device):
         rc = getattr(L, f"dtmpc_plant_step_{sfx}")(C.byref(env_c), C.byref(n_c), C.byref(a_c), B, _ptr(Un), _ptr(Ua),
-                                                   _ptr(theta_nom), tsn, _ptr(theta_aux), tsa, _ptr(w), _ptr(xh),
+                                                   _ptr(theta_nom), tsn, _ptr(theta_aux), tsa, _ptr(w),
+                                                   C.byref(rng_c) if rng_c is not None else None, _ptr(xh),
                                                    _ptr(xh_bar), _ptr(Vn_ws), _ptr(Va_ws), _stream())
     _lib.check(rc, "dtmpc_plant_step")
+
+
+def math_selftest(x: Tensor) -> Tensor:
+    """[n,6] = exp_nonpos(-|x|), log_ge1(1+|x|), log_1to2(1+frac|x|), sin x, cos x, rcp x of the library's fp64 functions."""
+    L = _lib.load()
+    x = _chk(x, tuple(x.shape), torch.float64, "x").reshape(-1)
+    out = torch.empty(x.numel(), 6, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.dtmpc_math_selftest_f64(_ptr(x), x.numel(), _ptr(out), _stream())
+    _lib.check(rc, "dtmpc_math_selftest")
+    return out
 
 
 def kernel_launches() -> int:

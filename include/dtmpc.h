@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DTMPC_ABI_VERSION 2
+#define DTMPC_ABI_VERSION 3
 #define DTMPC_MAX_OBS 16
 #define DTMPC_MAX_ALPHAS 8
 #define DTMPC_NTHETA 12
@@ -53,7 +53,8 @@ enum {
 enum {
     DTMPC_ST_OK = 0,
     DTMPC_ST_NONFINITE = 1,      /* reference: FloatingPointError (core/ddp.py:142,159) */
-    DTMPC_ST_NO_CANDIDATE = 2,   /* reference: RuntimeError (core/ddp.py:298-299)       */
+    DTMPC_ST_NO_CANDIDATE = 2,   /* reference: RuntimeError (core/ddp.py:298-299); reserved: only reachable with a
+                                    feasible_fn, which no reference caller passes and this ABI does not take */
     DTMPC_ST_AUX_SHIFT = 4       /* tube solve: aux status = (status >> 4) & 15        */
 };
 
@@ -105,9 +106,15 @@ typedef struct dtmpc_solve_io {
     int32_t *alpha_idx;             /* [B,max_iter] out, optional: accepted step index per iteration */
     void *costs;                    /* real [B,max_iter] out, optional: accepted cost per iteration  */
     void *margins;                  /* real [B,max_iter] out, optional: second-best minus best cost  */
+    int32_t *fail_at;               /* [B,2] out, optional: where the first non-finite value appeared, */
+                                    /* as the reference prints it (core/ddp.py:138-159, 230-235):      */
+                                    /* (iteration, step).  step = horizon index of the first non-finite */
+                                    /* feed-forward gain of that iteration's backward pass, or -1 when  */
+                                    /* a line-search / rollout cost was non-finite; (-1,-1) = clean     */
 } dtmpc_solve_io;
 
-/* Buffers of one batched sensitivity sweep + IFT accumulation. */
+/* Buffers of one batched sensitivity sweep + IFT accumulation.  X, V, Uref, gu, Xbar, dX, dV, dL, gUref must be
+ * 16-byte aligned (state / control rows move as vectors; cudaMalloc and torch allocations are). */
 typedef struct dtmpc_sens_io {
     const void *X, *V;              /* real [B,T+1,4], [B,T,2]: the lower-level optimum               */
     const void *theta;              /* real [B,12] or [12]                                           */
@@ -128,8 +135,13 @@ typedef struct dtmpc_sens_io {
                                     /* component: lets gXref of one sweep drive the next one)        */
 } dtmpc_sens_io;
 
-/* Thread safety: entry points may be called from several host threads (errors are thread-local; chunked solves
- * serialise their enqueue on an internal lock).  All work is asynchronous on the caller's stream. */
+/* Thread safety and internal state.  Entry points may be called from several host threads (errors are thread-local).
+ * The library owns no device memory, but it does keep, per device, a small pool of non-blocking CUDA streams and
+ * events (created on first use, never destroyed): batches of >= 16,384 instances are cut into up to 4 contiguous
+ * chunks that run on those streams, forked from and joined to the caller's stream by events, so the call is still
+ * ordered on `stream` like any other and may be captured into a CUDA graph.  The pool's events are shared by the
+ * calls on a device, so the ENQUEUE of a chunked call holds a per-device lock (the kernels of different calls still
+ * overlap on the GPU).  DTMPC_CHUNKS=1 in the environment disables chunking (and with it every internal stream). */
 int dtmpc_abi_version(void);
 const char *dtmpc_last_error(void);
 /* Number of CUDA kernels this library has enqueued in this process so far (all entry points, all streams). */
@@ -141,6 +153,11 @@ size_t dtmpc_solve_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_
 size_t dtmpc_sens_workspace_bytes(int32_t T, int64_t B, int32_t elem_size);
 size_t dtmpc_step_workspace_bytes(int32_t T, int64_t B, int32_t n_alpha, int32_t elem_size);
 size_t dtmpc_reduce_workspace_bytes(int64_t B, int32_t ncols, int32_t elem_size);
+
+/* Evaluates the library's fp64 elementary functions on n arguments (test hook for the <= 2 ulp claim of the
+ * hand-written exp / log / sincos / reciprocal that replace libdevice's on the rollout path):
+ * out [n,6] = exp_nonpos(-|x|), log_ge1(1 + |x|), log_1to2(1 + frac(|x|)), sin(x), cos(x), rcp(x). */
+int dtmpc_math_selftest_f64(const void *x, int64_t n, void *out, void *stream);
 
 /* ilqr_solve for B instances -- reference core/ddp.py:102-307 (clamp, rollout, <= max_iter x
  * [linearise :172-205, backward Riccati :208-254, all-alpha forward line search :256-301, tol break :303]). */
@@ -173,7 +190,11 @@ int dtmpc_tube_step_f32(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_
                         const dtmpc_sens_io *sens_nom, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ddp_sensitivity (reference core/ddp.py:317-427) fused with the IFT accumulation
- * (reference core/ift.py:35-92, closed forms; paper mode core/tube_mpc.py:965-976). */
+ * (reference core/ift.py:35-92, closed forms; paper mode core/tube_mpc.py:965-976).
+ * Precondition: X is the rollout of V through f_hat (X[k+1] = f_hat(X[k], V[k]), as every solve of this library
+ * returns it and as the reference's own call sites pass it).  The kernels take h and grad h of the successor state
+ * from the stored X[k+1]; the reference recomputes f(X[k], V[k]), which differs only for an inconsistent (X, V).
+ * One of Xref / target is required (the cost reference of the sweep). */
 int dtmpc_sensitivity_f64(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_sens_io *io,
                           void *workspace, size_t workspace_bytes, void *stream);
 int dtmpc_sensitivity_f32(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, const dtmpc_sens_io *io,
@@ -212,16 +233,27 @@ int dtmpc_primitives_f32(const dtmpc_env *env, const dtmpc_ocp *ocp, int64_t B, 
                          void *Bm, void *h, void *grad_h, void *cost, void *u_clamped, int32_t *active,
                          void *b0, void *stream);
 
+/* Disturbance drawn inside the plant step when no w tensor is passed (reference core/systems/dubins.py:57-65:
+ * w = low + (high - low) * U[0,1)^3).  Philox4x32-10, key = seed, counter = (first_instance + i, *step, draw): a pure
+ * function of (seed, global instance, step), hence independent of batch size, sharding and CUDA-graph replay. */
+typedef struct dtmpc_disturbance {
+    double low[3], high[3];
+    uint64_t seed;
+    int64_t first_instance;         /* global index of instance 0 of this call (offset of the rank's shard)     */
+    const int64_t *step;            /* DEVICE counter t of the closed-loop step, read at kernel run time        */
+} dtmpc_disturbance;
+
 /* Closed-loop plant step for B tubes (reference core/tube_mpc.py:990-1023): x+ = f(x,u0)+w, b+ from the
- * undisturbed successor, nominal propagation, warm-start shift.  In-place on xh/xh_bar/V*_ws. */
+ * undisturbed successor, nominal propagation, warm-start shift.  In-place on xh/xh_bar/V*_ws.
+ * w [B,3] (device) or NULL; with w == NULL and rng != NULL the disturbance is generated in the kernel. */
 int dtmpc_plant_step_f64(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,
                          const void *Un, const void *Ua, const void *theta_n, int64_t theta_n_stride,
-                         const void *theta_a, int64_t theta_a_stride, const void *w, void *xh, void *xh_bar,
-                         void *Vn_ws, void *Va_ws, void *stream);
+                         const void *theta_a, int64_t theta_a_stride, const void *w, const dtmpc_disturbance *rng,
+                         void *xh, void *xh_bar, void *Vn_ws, void *Va_ws, void *stream);
 int dtmpc_plant_step_f32(const dtmpc_env *env, const dtmpc_ocp *nom, const dtmpc_ocp *aux, int64_t B,
                          const void *Un, const void *Ua, const void *theta_n, int64_t theta_n_stride,
-                         const void *theta_a, int64_t theta_a_stride, const void *w, void *xh, void *xh_bar,
-                         void *Vn_ws, void *Va_ws, void *stream);
+                         const void *theta_a, int64_t theta_a_stride, const void *w, const dtmpc_disturbance *rng,
+                         void *xh, void *xh_bar, void *Vn_ws, void *Va_ws, void *stream);
 
 /* FP64 FMA peak of the current device (dependent-chain-free DFMA loop), TFLOP/s; used by bench.py as the
  * roofline denominator because MEASURED_PEAKS.json has no FP64 figure.  Synchronous. */

@@ -495,6 +495,10 @@ def main():
         "paper_T20": ([dict(i, T=20) for i in random_instances(12, 31337, cfg, vary_weights=True, h_min=0.05)], "paper", 2),
         "random_paper_f32": ([dict(i, fp32=True) for i in random_instances(32, 2024, cfg, h_min=1.0)], "paper", 1),
         "random_full_f32": ([dict(i, fp32=True) for i in random_instances(16, 4242, cfg, h_min=1.0)], "full", 1),
+        # the SAME instances as the two fp32 sets, solved by the reference in fp64: the reference's own fp32-vs-fp64 gap per
+        # instance is the yardstick the fp32 parity test measures the CUDA fp32 mode with
+        "random_paper_f32_ref64": (random_instances(32, 2024, cfg, h_min=1.0), "paper", 1),
+        "random_full_f32_ref64": (random_instances(16, 4242, cfg, h_min=1.0), "full", 1),
         "full_gamma": ([dict(i, T=20, dbas=dict(alpha=-1.0, gamma=g, nominal_tightening=-2.0))
                         for i, g in zip(random_instances(8, 555, cfg, h_min=0.02), (0.5, -0.5, 0.9, -0.9, 0.3, -0.3, 1.5, -1.5))],
                        "full", 2),

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(lib):
     exported = set(re.findall(r"\bT (dtmpc_[a-z0-9_]+)", out))
     missing = [f for f in _declared_functions() if f not in exported]
     assert not missing, missing
-    assert lib.dtmpc_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.dtmpc_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_library_is_sm100a_native():
@@ -56,7 +56,8 @@ def test_library_is_sm100a_native():
 def test_struct_layouts_match_the_header(tmp_path):
     from differentiable_tube_mpc_b200 import _lib
 
-    structs = {"dtmpc_env": _lib.Env, "dtmpc_ocp": _lib.Ocp, "dtmpc_solve_io": _lib.SolveIO, "dtmpc_sens_io": _lib.SensIO}
+    structs = {"dtmpc_env": _lib.Env, "dtmpc_ocp": _lib.Ocp, "dtmpc_solve_io": _lib.SolveIO, "dtmpc_sens_io": _lib.SensIO,
+               "dtmpc_disturbance": _lib.Disturbance}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

@@ -44,11 +44,23 @@ def _worker(rank, world, port, q):
         for full in (False, True):
             st = allreduce_shared(_fake_step(g_all[lo:hi], loss_all[lo:hi], full))
             out[full] = (st.g_aux_sum.clone(), None if st.g_nom_sum is None else st.g_nom_sum.clone())
+        # a graphed step hands out the SAME static tensors on every replay, refilled in place: repeated reductions of
+        # one TubeStep must reduce the fresh values, not an already reduced copy (round-1 bug: the sums grew world x)
+        st = _fake_step(g_all[lo:hi], loss_all[lo:hi], True)
+        keep_aux, keep_nom = st.g_aux_sum, st.g_nom_sum
+        reps = []
+        for rep in range(3):
+            fresh = _fake_step(g_all[lo:hi] * (rep + 1), loss_all[lo:hi], True)
+            keep_aux.copy_(fresh.g_aux_sum)
+            keep_nom.copy_(fresh.g_nom_sum)
+            allreduce_shared(st)
+            assert st.g_aux_sum is keep_aux and st.g_nom_sum is keep_nom
+            reps.append((keep_aux.clone().numpy(), keep_nom.clone().numpy()))
         ad = PaperAdapter(Qa=torch.ones(3, dtype=torch.float64), Ra=torch.ones(2, dtype=torch.float64),
                           qba=torch.tensor(1.0, dtype=torch.float64), eta=0.05, mom=0.9)
         ad.update(out[False][0][:12] / total)
         q.put((rank, lo, hi, float(x_loc.sum()), out[False][0].numpy(), out[True][0].numpy(), out[True][1].numpy(),
-               ad.theta().numpy()))
+               ad.theta.numpy(), reps))
     finally:
         dist.destroy_process_group()
 
@@ -76,6 +88,10 @@ def test_world_size_2_sharding_and_allreduce():
         assert np.allclose(r[4], want13, rtol=1e-13, atol=1e-12)          # paper mode: 12 gradients + loss
         assert np.allclose(r[5], want13, rtol=1e-13, atol=1e-12)          # full mode, theta part
         assert np.allclose(r[6], 2.0 * g_all.sum(0).numpy(), rtol=1e-13, atol=1e-12)  # full mode, theta_bar part
+        for rep, (ga, gn) in enumerate(r[8]):
+            assert np.allclose(ga[:12], (rep + 1) * want13[:12], rtol=1e-13, atol=1e-12), rep
+            assert np.allclose(gn, 2.0 * (rep + 1) * g_all.sum(0).numpy(), rtol=1e-13, atol=1e-12), rep
+    assert all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(res[0][8], res[1][8]))
     # identical reduced gradient -> bitwise identical parameter update on every rank
     assert np.array_equal(res[0][4], res[1][4]) and np.array_equal(res[0][7], res[1][7])
 

@@ -285,6 +285,30 @@ def test_fp32_mode_against_the_reference_float32_run(name):
               f"all instances median {np.median(e):.1e}")
         assert np.median(e[good]) < 1e-4, (key, np.median(e[good]))
         assert e[good].max() < 5e-3, (key, e[good].max())
+    # ---- the honest pin (round 2) ---------------------------------------------------------------------------------
+    # fp32 decisions are roundoff ties almost everywhere near convergence (candidate costs equal to 1-8 ulp_fp32, the
+    # tolerance break decided by whether two fp32 costs are bitwise equal), so "same decisions" cannot define the
+    # comparable set.  The yardstick is the reference itself: delta_i = how far the reference's OWN fp32 run is from its
+    # fp64 run on instance i (goldens *_f32_ref64: the same instances solved by the reference in fp64).  Where the
+    # reference's two precisions agree to a quarter of the tolerance the instance is well-posed in fp32, and the CUDA
+    # fp32 mode must be within 1e-4 (MAX, not median) of both reference runs; elsewhere it must be no further from the
+    # fp32 reference than 1e-4 + 4 delta_i.
+    g64 = load_golden(name + "_ref64")
+    assert np.allclose(g64["x0"], g["x0"])
+    keys = (("nom_X", rn.X), ("nom_V", rn.V), ("aux_X", ra.X), ("aux_V", ra.V))
+    delta = np.max([per_instance_rel(g[k][:, 0], g64[k][:, 0], floor=1e-3) for k, _ in keys], axis=0)
+    pin = delta <= 2.5e-5
+    hist = np.histogram(np.log10(np.maximum(delta, 1e-9)), bins=[-9, -7, -6, -5, -4.6, -4, -3, -2, 0])[0]
+    print(f"[fp32 {name}] reference fp32-vs-fp64 gap per instance: log10 histogram (-9,-7,-6,-5,-4.6,-4,-3,-2,0) = {hist.tolist()}; "
+          f"pinned {pin.sum()}/{n}")
+    assert pin.sum() >= (0.4 if mode == "paper" else 0.75) * n
+    for key, got in keys:
+        e32 = per_instance_rel(got.double().cpu().numpy(), g[key][:, 0], floor=1e-3)
+        e64 = per_instance_rel(got.double().cpu().numpy(), g64[key][:, 0], floor=1e-3)
+        print(f"[fp32 {name}] {key}: pinned max vs ref32 {e32[pin].max():.1e}, vs ref64 {e64[pin].max():.1e}; "
+              f"unpinned max excess over 4 delta {np.max(e32[~pin] - 4 * delta[~pin], initial=0.0):.1e}")
+        assert e32[pin].max() < 1e-4 and e64[pin].max() < 1e-4, (key, e32[pin].max(), e64[pin].max())
+        assert np.all(e32[~pin] <= 1e-4 + 4 * delta[~pin]), (key, np.max(e32[~pin] - 4 * delta[~pin]))
     # sensitivity + gradients at the reference's own fp32 optimum
     Xa, Ua, Xn, Un = c32("aux_X"), c32("aux_V"), c32("nom_X"), c32("nom_V")
     sa = ops.ddp_sensitivity_batched(prob.system, prob.auxiliary, Xa, Ua, c32("aux_theta"), X_bar=Xn, X_ref=Xn, U_ref=Un,

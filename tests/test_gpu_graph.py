@@ -75,8 +75,8 @@ def test_launch_counter_counts_kernels():
     n0 = ops.kernel_launches()
     eng.step(*args, full=False)
     torch.cuda.synchronize()
-    # init + max_iter x (ric, fwd, commit) per OCP, one sensitivity sweep, two reduction kernels
-    expect = (1 + 3 * p.nominal.ilqr.max_iter) + (1 + 3 * p.auxiliary.ilqr.max_iter) + 1 + 2   # B = 512: one chunk
+    # init + max_iter x (ric, fwdc = line search + selection + commit) per OCP, one sensitivity sweep, two reduction kernels
+    expect = (1 + 2 * p.nominal.ilqr.max_iter) + (1 + 2 * p.auxiliary.ilqr.max_iter) + 1 + 2   # B = 512: one chunk
     assert ops.kernel_launches() - n0 == expect
 
 

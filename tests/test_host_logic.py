@@ -93,7 +93,7 @@ def test_paper_adapter_reproduces_the_reference_update():
         g12 = torch.zeros(12, dtype=torch.float64)
         g12[0:3], g12[3:5], g12[8] = torch.tensor(g["gQ"][0, t]), torch.tensor(g["gR"][0, t]), torch.tensor(g["gqb"][0, t])
         ad.update(g12)
-        assert rel_err(ad.theta().numpy(), th[t + 1]) < 1e-15, t
+        assert rel_err(ad.theta.numpy(), th[t + 1]) < 1e-15, t
     gQ, gR, gqb = PaperAdapter.grads_from_g12(torch.arange(12.0))
     assert gQ.tolist() == [5.0, 7.0, 9.0] and gR.tolist() == [3.0, 4.0] and float(gqb) == 8.0
 

@@ -22,7 +22,7 @@ except Exception as e:
 PY
   if [ "${NCU:-0}" = "1" ]; then
     DTMPC_LIB="$lib" DTMPC_CHUNKS=1 ncu --metrics smsp__inst_executed.sum,sm__inst_executed_pipe_fp64.sum,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
-      --clock-control none -k regex:'fwd_kernel|ric_kernel|commit_kernel|sens_kernel|init_kernel' -c 16 --csv \
+      --clock-control none -k regex:'fwdc?_kernel|ric_kernel|commit_kernel|sens_kernel|init_kernel' -c ${NCU_COUNT:-16} --csv \
       --log-file "gpurun_out/ab_${v}_inst.csv" python tools/step_times.py --steps 1 ${STEP_ARGS:-} > "gpurun_out/ab_${v}_ncu.log" 2>&1
   fi
 done

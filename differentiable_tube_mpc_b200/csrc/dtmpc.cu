@@ -143,7 +143,7 @@ bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
 // stream-ordered; the host never waits, so all max_iter iterations are enqueued and the ones that find the
 // slots all vacated return at once.
 // candidates rolled out per thread of the line-search kernel (DTMPC_FWD_NC overrides, for tuning)
-int fwd_candidates_per_thread(int n_eval) {
+[[maybe_unused]] int fwd_candidates_per_thread(int n_eval) {
     static int forced = -1;
     if (forced < 0) {
         const char *e = getenv("DTMPC_FWD_NC");
@@ -177,7 +177,13 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     static const bool allow_fixed = !getenv("DTMPC_NO_FIXED_NOBS");
     const int fixed_nobs = (allow_fixed && P.env.agg == DTMPC_AGG_SMOOTHMIN) ? P.env.n_obs : -1;
     P.parity = 0;
-    init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+#define DTMPC_INIT_CASE(N) case N: init_kernel<R, N><<<gB, LS_BLOCK, 0, st>>>(P); break;
+    switch (fixed_nobs) {
+        DTMPC_INIT_CASE(1) DTMPC_INIT_CASE(2) DTMPC_INIT_CASE(3) DTMPC_INIT_CASE(4)
+        DTMPC_INIT_CASE(5) DTMPC_INIT_CASE(6) DTMPC_INIT_CASE(7) DTMPC_INIT_CASE(8)
+        default: init_kernel<R><<<gB, LS_BLOCK, 0, st>>>(P);
+    }
+#undef DTMPC_INIT_CASE
     const unsigned gFwd = (unsigned)((B + 31) / 32);
     const unsigned gRic = (unsigned)((B + RIC_BLOCK - 1) / RIC_BLOCK);
 #if DTMPC_FUSED_COMMIT
@@ -229,7 +235,11 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
                 }
             }
 #undef DTMPC_FWD_CASE
-            else if (nc == 2) fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
+            else if (nc == 2) {
+                if (fixed_nobs == 5 && P.use_ref) fwd_kernel<R, 2, 5, 1><<<gFwd, blk, 0, st>>>(P);
+                else if (fixed_nobs == 5) fwd_kernel<R, 2, 5, 0><<<gFwd, blk, 0, st>>>(P);
+                else fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
+            }
             else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);
         }
         // the last iteration retires every instance still running
@@ -292,6 +302,17 @@ template <typename R> void offset_sens_io(SensArgs<R> &a, long long off, int T) 
     if (a.status) a.status += off;
 }
 
+template <typename R> void launch_sens_kernel(const SensParams<R> &P, unsigned grid, cudaStream_t st) {
+    static const bool allow_fixed = !getenv("DTMPC_NO_FIXED_NOBS");
+#define DTMPC_SENS_CASE(N) case N: sens_kernel<R, N><<<grid, SENS_BLOCK, 0, st>>>(P); break;
+    switch ((allow_fixed && P.env.agg == DTMPC_AGG_SMOOTHMIN) ? P.env.n_obs : -1) {
+        DTMPC_SENS_CASE(1) DTMPC_SENS_CASE(2) DTMPC_SENS_CASE(3) DTMPC_SENS_CASE(4)
+        DTMPC_SENS_CASE(5) DTMPC_SENS_CASE(6) DTMPC_SENS_CASE(7) DTMPC_SENS_CASE(8)
+        default: sens_kernel<R><<<grid, SENS_BLOCK, 0, st>>>(P);
+    }
+#undef DTMPC_SENS_CASE
+}
+
 // sensitivity sweep of instances [off, off + Bc) on stream st, scratch at ws (sens_ws_rows(T) rows of whole tiles)
 template <typename R>
 int launch_sens_chunk(const dtmpc_env *env, const dtmpc_ocp *ocp, const dtmpc_sens_io *io, long long off, long long Bc,
@@ -304,7 +325,7 @@ int launch_sens_chunk(const dtmpc_env *env, const dtmpc_ocp *ocp, const dtmpc_se
     offset_sens_io(P.io, off, ocp->horizon);
     P.B = Bc;
     P.ws = (R *)ws;
-    sens_kernel<R><<<(unsigned)((Bc + SENS_BLOCK - 1) / SENS_BLOCK), SENS_BLOCK, 0, st>>>(P);
+    launch_sens_kernel<R>(P, (unsigned)((Bc + SENS_BLOCK - 1) / SENS_BLOCK), st);
     count_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "sensitivity kernel launch");
@@ -495,7 +516,7 @@ int sens_impl(const dtmpc_env *env, const dtmpc_ocp *ocp, long long B, const dtm
         if (ws_bytes < dtmpc_sens_workspace_bytes(ocp->horizon, B, (int)sizeof(R)))
             return fail(DTMPC_E_WORKSPACE, "sensitivity workspace too small");
         P.ws = (R *)ws;
-        sens_kernel<R><<<grid, SENS_BLOCK, 0, st>>>(P);
+        launch_sens_kernel<R>(P, grid, st);
     }
     count_launches(1);
     cudaError_t e = cudaGetLastError();

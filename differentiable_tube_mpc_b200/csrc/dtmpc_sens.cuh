@@ -86,7 +86,8 @@ template <typename R> __device__ __forceinline__ void store_grads(R *out, const 
     out[8] = g.gqb; out[9] = g.ga; out[10] = g.gg; out[11] = g.gt;
 }
 
-template <typename R>
+// NOBS > 0: obstacle count of a smooth-min environment fixed at compile time (as in the solver kernels)
+template <typename R, int NOBS = -1>
 __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant__ SensParams<R> P) {
     using m = M<R>;
     const long long i = (long long)blockIdx.x * SENS_BLOCK + threadIdx.x;
@@ -139,18 +140,26 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         V00 = R(2) * th.Qf0; V11 = R(2) * th.Qf1; V22 = R(2) * th.Qf2; V33 = R(2) * th.qb;
         V01 = V02 = V03 = V10 = V12 = V13 = V20 = V21 = V23 = V30 = V31 = V32 = R(0);
         R hT;
-        barrier_grad(E, th, px, py, gnx, gny, hT);
+        barrier_grad<R, NOBS>(E, th, px, py, gnx, gny, hT);
         WS(ROW(T, 0)) = hT;
     }
     const R lxx0 = R(2) * th.Q0, lxx1 = R(2) * th.Q1, lxx2 = R(2) * th.Q2, lxx3 = R(2) * th.qb;
     const R luu0 = R(2) * th.R0, luu1 = R(2) * th.R1;
     const R sreg = R(1e-9);  // core/ddp.py:373
+    // one running pointer per stream (scratch rows of step k, state / control rows of the instance): every access is
+    // pointer + immediate; indexing by k cost ~4 integer instructions of 64-bit address arithmetic per access
+    R *wk = ws + (long long)T * (SENS_ROWS * 32);
+    const R *Xk = X + 4LL * T, *Vk = V + 2LL * T;
     for (int k = T - 1; k >= 0; --k) {
+        wk -= SENS_ROWS * 32;
+        Xk -= 4;
+        Vk -= 2;
+#define WK(r) wk[(r) * 32]
         R px, py, pt, pb, u0, u1;
-        ld4(X + 4 * k, px, py, pt, pb);
-        ld2(V + 2 * k, u0, u1);
+        ld4(Xk, px, py, pt, pb);
+        ld2(Vk, u0, u1);
         R gcx, gcy, hk;
-        barrier_grad(E, th, px, py, gcx, gcy, hk);
+        barrier_grad<R, NOBS>(E, th, px, py, gcx, gcy, hk);
         Lin<R> L;
         linearize(E, th, pt, u0, gnx, gny, gcx, gcy, L);
         gnx = gcx;
@@ -238,19 +247,18 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         ENT_V(2, 0) ENT_V(2, 1) ENT_V(2, 2) ENT_V(2, 3)
         ENT_V(3, 0) ENT_V(3, 1) ENT_V(3, 2) ENT_V(3, 3)
 #undef ENT_V
-        // stash for the forward sweep
-        int r = ROW(k, 1);
-        WS(r + 0) = K00; WS(r + 1) = K01; WS(r + 2) = K02; WS(r + 3) = K03;
-        WS(r + 4) = K10; WS(r + 5) = K11; WS(r + 6) = K12; WS(r + 7) = K13;
-        WS(r + 8) = k0; WS(r + 9) = k1;
-        WS(r + 10) = Vx0; WS(r + 11) = Vx1; WS(r + 12) = Vx2; WS(r + 13) = Vx3;
-        WS(r + 14) = V00; WS(r + 15) = V01; WS(r + 16) = V02; WS(r + 17) = V03;
-        WS(r + 18) = V10; WS(r + 19) = V11; WS(r + 20) = V12; WS(r + 21) = V13;
-        WS(r + 22) = V20; WS(r + 23) = V21; WS(r + 24) = V22; WS(r + 25) = V23;
-        WS(r + 26) = V30; WS(r + 27) = V31; WS(r + 28) = V32; WS(r + 29) = V33;
-        WS(r + 30) = L.a02; WS(r + 31) = L.a12; WS(r + 32) = L.r0; WS(r + 33) = L.r1;
-        WS(r + 34) = L.r2; WS(r + 35) = L.b00; WS(r + 36) = L.b10; WS(r + 37) = L.s0;
-        WS(ROW(k, 0)) = hk;
+        // stash for the forward sweep (row 0: h, rows 1..38 below)
+        WK(1) = K00; WK(2) = K01; WK(3) = K02; WK(4) = K03;
+        WK(5) = K10; WK(6) = K11; WK(7) = K12; WK(8) = K13;
+        WK(9) = k0; WK(10) = k1;
+        WK(11) = Vx0; WK(12) = Vx1; WK(13) = Vx2; WK(14) = Vx3;
+        WK(15) = V00; WK(16) = V01; WK(17) = V02; WK(18) = V03;
+        WK(19) = V10; WK(20) = V11; WK(21) = V12; WK(22) = V13;
+        WK(23) = V20; WK(24) = V21; WK(25) = V22; WK(26) = V23;
+        WK(27) = V30; WK(28) = V31; WK(29) = V32; WK(30) = V33;
+        WK(31) = L.a02; WK(32) = L.a12; WK(33) = L.r0; WK(34) = L.r1;
+        WK(35) = L.r2; WK(36) = L.b00; WK(37) = L.b10; WK(38) = L.s0;
+        WK(0) = hk;
     }
 
     // ---- forward sweep (core/ddp.py:412-425) + gradient accumulation ---------
@@ -265,14 +273,16 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     // carried from step k-1 for the dynamics term of the accumulation
     R p_px = 0, p_py = 0, p_pt = 0, p_pb = 0, p_u0 = 0, p_u1 = 0, p_r0 = 0, p_r1 = 0, p_r2 = 0, p_q0 = 0, p_q1 = 0;
     R p_d0 = 0, p_d1 = 0, p_d2 = 0, p_d3 = 0, p_du0 = 0, p_du1 = 0, p_h = 0;
+    // wk, Xk, Vk stand at step 0 after the backward sweep
+    const R *xrk = xrp, *urk = urp, *Xbk = Xb;
+    R *dXk = dXo, *dVk = dVo, *dLk = dLo, *gxk = gxo, *guk = guo;
     for (int k = 0; k < T; ++k) {
-        const int r = ROW(k, 1);
-        const R K00 = WS(r + 0), K01 = WS(r + 1), K02 = WS(r + 2), K03 = WS(r + 3);
-        const R K10 = WS(r + 4), K11 = WS(r + 5), K12 = WS(r + 6), K13 = WS(r + 7);
-        const R k0 = WS(r + 8), k1 = WS(r + 9);
+        const R K00 = WK(1), K01 = WK(2), K02 = WK(3), K03 = WK(4);
+        const R K10 = WK(5), K11 = WK(6), K12 = WK(7), K13 = WK(8);
+        const R k0 = WK(9), k1 = WK(10);
         R px, py, pt, pb, u0, u1;
-        ld4(X + 4 * k, px, py, pt, pb);
-        ld2(V + 2 * k, u0, u1);
+        ld4(Xk, px, py, pt, pb);
+        ld2(Vk, u0, u1);
         bool a0, a1;
         active_u(E, u0, u1, a0, a1);
         R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
@@ -280,20 +290,21 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         if (a0) du0 = R(0);
         if (a1) du1 = R(0);
         // delta_lambda_k = tilde V_x,k + V_xx,k delta_x_k
-        const R l0 = WS(r + 10) + m::fma_(WS(r + 17), d3, m::fma_(WS(r + 16), d2, m::fma_(WS(r + 15), d1, WS(r + 14) * d0)));
-        const R l1 = WS(r + 11) + m::fma_(WS(r + 21), d3, m::fma_(WS(r + 20), d2, m::fma_(WS(r + 19), d1, WS(r + 18) * d0)));
-        const R l2 = WS(r + 12) + m::fma_(WS(r + 25), d3, m::fma_(WS(r + 24), d2, m::fma_(WS(r + 23), d1, WS(r + 22) * d0)));
-        const R l3 = WS(r + 13) + m::fma_(WS(r + 29), d3, m::fma_(WS(r + 28), d2, m::fma_(WS(r + 27), d1, WS(r + 26) * d0)));
-        st4(dXo + 4 * k, d0, d1, d2, d3);
-        st2(dVo + 2 * k, du0, du1);
-        st4(dLo + 4 * k, l0, l1, l2, l3);
+        const R l0 = WK(11) + m::fma_(WK(18), d3, m::fma_(WK(17), d2, m::fma_(WK(16), d1, WK(15) * d0)));
+        const R l1 = WK(12) + m::fma_(WK(22), d3, m::fma_(WK(21), d2, m::fma_(WK(20), d1, WK(19) * d0)));
+        const R l2 = WK(13) + m::fma_(WK(26), d3, m::fma_(WK(25), d2, m::fma_(WK(24), d1, WK(23) * d0)));
+        const R l3 = WK(14) + m::fma_(WK(30), d3, m::fma_(WK(29), d2, m::fma_(WK(28), d1, WK(27) * d0)));
+        st4(dXk, d0, d1, d2, d3);
+        st2(dVk, du0, du1);
+        st4(dLk, l0, l1, l2, l3);
         bad |= !finite_((l0 + l1) + (l2 + l3) + (du0 + du1));
-        const R hk = WS(ROW(k, 0));
+        const R hk = WK(0);
         R r0, r1, r2, q0, q1;
         if (xrp) {
-            const R *xr = xrp + k * xrow;
-            r0 = xr[0]; r1 = xr[1]; r2 = xr[2];
-            ld2(urp + 2 * k, q0, q1);
+            r0 = xrk[0]; r1 = xrk[1]; r2 = xrk[2];
+            ld2(urk, q0, q1);
+            xrk += xrow;
+            urk += 2;
         } else {
             const R *tp = a.target + i * a.target_stride;
             r0 = tp[0]; r1 = tp[1]; r2 = tp[2];
@@ -303,13 +314,17 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
             accumulate_stage(th, jc, G, aw, p_px, p_py, p_pt, p_pb, p_u0, p_u1, p_r0, p_r1, p_r2, p_q0, p_q1, p_d0, p_d1, p_d2,
                              p_d3, p_du0, p_du1, l3, p_h, hk);
         if (gxo) {
-            R *o = gxo + 3 * k;
-            o[0] = -(R(2) * th.Q0) * d0; o[1] = -(R(2) * th.Q1) * d1; o[2] = -(R(2) * th.Q2) * d2;
+            gxk[0] = -(R(2) * th.Q0) * d0; gxk[1] = -(R(2) * th.Q1) * d1; gxk[2] = -(R(2) * th.Q2) * d2;
+            gxk += 3;
         }
-        if (guo) st2(guo + 2 * k, -(R(2) * th.R0) * du0, -(R(2) * th.R1) * du1);
+        if (guo) {
+            st2(guk, -(R(2) * th.R0) * du0, -(R(2) * th.R1) * du1);
+            guk += 2;
+        }
         if (a.loss && Xb) {
             R b0, b1, b2, b3;
-            ld4(Xb + 4 * k, b0, b1, b2, b3);
+            ld4(Xbk, b0, b1, b2, b3);
+            Xbk += 4;
             const R e0 = px - b0, e1 = py - b1, e2 = pt - b2;
             loss_t += m::fma_(e2, e2, m::fma_(e1, e1, e0 * e0));
             loss_b = m::fma_(pb, pb, loss_b);
@@ -318,14 +333,21 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         p_r0 = r0; p_r1 = r1; p_r2 = r2; p_q0 = q0; p_q1 = q1;
         p_d0 = d0; p_d1 = d1; p_d2 = d2; p_d3 = d3; p_du0 = du0; p_du1 = du1; p_h = hk;
         // delta_x_{k+1} = A delta_x_k + B delta_u_k
-        const R a02 = WS(r + 30), a12 = WS(r + 31), R0 = WS(r + 32), R1 = WS(r + 33), R2 = WS(r + 34);
-        const R b00 = WS(r + 35), b10 = WS(r + 36), s0 = WS(r + 37);
+        const R a02 = WK(31), a12 = WK(32), R0 = WK(33), R1 = WK(34), R2 = WK(35);
+        const R b00 = WK(36), b10 = WK(37), s0 = WK(38);
         const R n0 = m::fma_(b00, du0, m::fma_(a02, d2, d0));
         const R n1 = m::fma_(b10, du0, m::fma_(a12, d2, d1));
         const R n2 = m::fma_(dt, du1, d2);
         const R n3 = m::fma_(s0, du0, m::fma_(gam, d3, m::fma_(R2, d2, m::fma_(R1, d1, R0 * d0))));
         d0 = n0; d1 = n1; d2 = n2; d3 = n3;
+        wk += SENS_ROWS * 32;
+        Xk += 4;
+        Vk += 2;
+        dXk += 4;
+        dVk += 2;
+        dLk += 4;
     }
+#undef WK
     {
         // terminal: delta_lambda_T = g_x,T + phi_xx delta_x_T   (core/ddp.py:425; V_xx,T = diag(2Qf, 2qb))
         R px, py, pt, pb;

@@ -145,7 +145,8 @@ __device__ __forceinline__ void ref_at(const SolveParams<R> &P, const R *rk, boo
 // ---------------------------------------------------------------------------------------------------------------
 // init: V = clamp(V_init), X = rollout(x0, V)  (core/ddp.py:125-131); every instance starts in slot i
 // ---------------------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(const __grid_constant__ SolveParams<R> P) {
+template <typename R, int NOBS = -1>
+__global__ void __launch_bounds__(LS_BLOCK) init_kernel(const __grid_constant__ SolveParams<R> P) {
     const long long i = (long long)blockIdx.x * LS_BLOCK + threadIdx.x;
     if (i == 0) {
         P.ws.counts[0] = (int)P.B;
@@ -178,7 +179,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
     X[EL(0, TR, 0)] = x.px; X[EL(0, TR, 1)] = x.py; X[EL(0, TR, 2)] = x.th; X[EL(0, TR, 3)] = x.b;
     {
         R g0x, g0y, h0;
-        barrier_grad(E, th, x.px, x.py, g0x, g0y, h0);
+        barrier_grad<R, NOBS>(E, th, x.px, x.py, g0x, g0y, h0);
         X[EL(0, TR, 6)] = g0x; X[EL(0, TR, 7)] = g0y;
     }
     const R *vp = P.io.V_init + i * (2LL * T);
@@ -192,7 +193,7 @@ template <typename R> __global__ void __launch_bounds__(LS_BLOCK) init_kernel(co
         ref_at(P, ref_i + EL(k, RR, 0), true, t0, t1, t2, r);
         J += stage_cost(th, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
         R gx, gy;
-        step_g(E, th, x, u0, u1, gx, gy);
+        step_g<R, NOBS>(E, th, x, u0, u1, gx, gy);
         X[EL(k + 1, TR, 0)] = x.px;
         X[EL(k + 1, TR, 1)] = x.py;
         X[EL(k + 1, TR, 2)] = x.th;
@@ -511,7 +512,10 @@ template <typename R> __device__ __forceinline__ void theta_fetch_jac(const R *s
 constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 
 template <typename R, int NC, int NOBS = -1, int UR = -1>
-__global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : 168) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
+#ifndef DTMPC_FWD2_MAXNREG
+#define DTMPC_FWD2_MAXNREG 168
+#endif
+__global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : DTMPC_FWD2_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     __shared__ R sJ[DTMPC_MAX_ALPHAS * 32];
     const int n_act = P.ws.counts[P.parity];
@@ -910,9 +914,25 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
     // ---- phase 1: candidate rollout, cost only -------------------------------------------------------------------
     State<R> x{X[EL(0, TR, 0)], X[EL(0, TR, 1)], X[EL(0, TR, 2)], X[EL(0, TR, 3)], P.ws.B0[i]};
     R J = R(0);
+    // Inputs of a rollout step: x_k, u_k (6 rows) and K_k, k_k (10 rows) of the slot.  The wait for them at the top of a
+    // step is the largest single stall of the kernel (ncu source view, profiles/r02_fwdc: 21 % of all stall samples sit
+    // on the first instructions that consume them).  Issuing the loads of step k+1 as soon as u_k is known (software
+    // pipelining through registers) was measured and rejected: the 16 values in flight push the kernel far over its
+    // 72-register budget (stack frame 104 -> 256 B) and the step went from 14.2 to 19.5 ms (18.3 ms at 80 registers).
+    struct StepIn {
+        R X0, X1, X2, X3, v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1;
+    };
+    auto load_in = [](const R *xp, const R *gp, StepIn &q) {
+        q.X0 = xp[0 * 32]; q.X1 = xp[1 * 32]; q.X2 = xp[2 * 32]; q.X3 = xp[3 * 32];
+        q.v0 = xp[4 * 32]; q.v1 = xp[5 * 32];
+        q.K00 = gp[0 * 32]; q.K01 = gp[1 * 32]; q.K02 = gp[2 * 32]; q.K03 = gp[3 * 32];
+        q.K10 = gp[4 * 32]; q.K11 = gp[5 * 32]; q.K12 = gp[6 * 32]; q.K13 = gp[7 * 32];
+        q.k0 = gp[8 * 32]; q.k1 = gp[9 * 32];
+    };
     {
         int k_ck = seg_len, seg = 0;
         const R *xp = X, *gp = GK, *rp = ref_i;
+        StepIn in;
         for (int k = 0; k < T; ++k) {
             if (k == k_ck) {  // phase 3 restarts the winner from here (uniform branch)
                 R *c = sCk + ((wy * (n_seg - 1) + seg) * CR) * 32 + lane;
@@ -920,25 +940,21 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
                 k_ck += seg_len;
                 ++seg;
             }
-            const R X0 = xp[0 * 32], X1 = xp[1 * 32], X2 = xp[2 * 32], X3 = xp[3 * 32];
-            const R v0 = xp[4 * 32], v1 = xp[5 * 32];
-            const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
-            const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
-            const R k0 = gp[8 * 32], k1 = gp[9 * 32];
+            load_in(xp, gp, in);
             RefPt<R> r;
             ref_at<R, UR>(P, rp, true, t0, t1, t2, r);
-            xp += TR * 32;
-            gp += GR * 32;
             rp += RR * 32;
             Theta<R> tk;
             tk.eps_dyn = P.ocp.eps_dyn; tk.angle_wrap = P.ocp.angle_wrap;
             theta_fetch(sTh, lane, tk);
             // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
-            const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
-            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
-            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-            R u0 = m::fma_(al, du0, v0), u1 = m::fma_(al, du1, v1);
+            const R d0 = x.px - in.X0, d1 = x.py - in.X1, d2 = x.th - in.X2, d3 = x.b - in.X3;
+            const R du0 = in.k0 + m::fma_(in.K03, d3, m::fma_(in.K02, d2, m::fma_(in.K01, d1, in.K00 * d0)));
+            const R du1 = in.k1 + m::fma_(in.K13, d3, m::fma_(in.K12, d2, m::fma_(in.K11, d1, in.K10 * d0)));
+            R u0 = m::fma_(al, du0, in.v0), u1 = m::fma_(al, du1, in.v1);
             clamp_u(E, u0, u1);
+            xp += TR * 32;
+            gp += GR * 32;
             J += stage_cost(tk, x.px, x.py, x.th, x.b, u0, u1, r.x0, r.x1, r.x2, r.u0, r.u1);
             State<R> xs[1] = {x};
             const R a0[1] = {u0}, a1[1] = {u1};
@@ -1041,33 +1057,54 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
     }
     const R *xp = X + EL(k_lo, TR, 0), *gp = GK + EL(k_lo, GR, 0);
     R *xn = Xn + EL(k_lo, TR, 0);
+    // inputs of a commit step: u_k, K_k, k_k and the OLD x_{k+1} (the next step's reference state, or, with g_{k+1},
+    // the copied successor)
+    struct CommitIn {
+        R v0, v1, K00, K01, K02, K03, K10, K11, K12, K13, k0, k1, N0, N1, N2, N3;
+    };
+    auto load_commit = [](const R *xp, const R *gp, CommitIn &q) {
+        q.v0 = xp[4 * 32]; q.v1 = xp[5 * 32];
+        q.K00 = gp[0 * 32]; q.K01 = gp[1 * 32]; q.K02 = gp[2 * 32]; q.K03 = gp[3 * 32];
+        q.K10 = gp[4 * 32]; q.K11 = gp[5 * 32]; q.K12 = gp[6 * 32]; q.K13 = gp[7 * 32];
+        q.k0 = gp[8 * 32]; q.k1 = gp[9 * 32];
+        q.N0 = xp[(TR + 0) * 32]; q.N1 = xp[(TR + 1) * 32]; q.N2 = xp[(TR + 2) * 32]; q.N3 = xp[(TR + 3) * 32];
+    };
+    CommitIn ci;
     for (int k = k_lo; k < k_hi; ++k) {
-        const R v0 = xp[4 * 32], v1 = xp[5 * 32];
-        const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
-        const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
-        const R k0 = gp[8 * 32], k1 = gp[9 * 32];
-        const R N0 = xp[(TR + 0) * 32], N1 = xp[(TR + 1) * 32];
-        const R N2 = xp[(TR + 2) * 32], N3 = xp[(TR + 3) * 32];
-        R u0 = v0, u1 = v1, gx, gy;
+        load_commit(xp, gp, ci);
+        const R K00 = ci.K00, K01 = ci.K01, K02 = ci.K02, K03 = ci.K03, K10 = ci.K10, K11 = ci.K11, K12 = ci.K12, K13 = ci.K13;
+        const R k0 = ci.k0, k1 = ci.k1, N0 = ci.N0, N1 = ci.N1, N2 = ci.N2, N3 = ci.N3;
+        R u0 = ci.v0, u1 = ci.v1, gx, gy;
         if (!copy) {
-            Theta<R> tk;
-            tk.eps_dyn = P.ocp.eps_dyn; tk.eps_jac = P.ocp.eps_jac; tk.angle_wrap = P.ocp.angle_wrap;
-            theta_fetch(sTh, lane, tk);
-            theta_fetch_jac(sTh, lane, tk);
             const R d0 = xw.px - X0, d1 = xw.py - X1, d2 = xw.th - X2, d3 = xw.b - X3;
             const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
             const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-            u0 = m::fma_(alw, du0, v0);
-            u1 = m::fma_(alw, du1, v1);
+            u0 = m::fma_(alw, du0, ci.v0);
+            u1 = m::fma_(alw, du1, ci.v1);
             clamp_u(E, u0, u1);
-            step_g<R, NOBS>(E, tk, xw, u0, u1, gx, gy);
         } else {
-            xw.px = N0; xw.py = N1; xw.th = N2; xw.b = N3;
             gx = xp[(TR + 6) * 32];
             gy = xp[(TR + 7) * 32];
         }
         xp += TR * 32;
         gp += GR * 32;
+        if (!keep) {   // a stopping instance returns the gains of its last backward pass (core/ddp.py:307)
+            if (P.io.K) {
+                R *Ko = P.io.K + i * (8LL * T) + 8 * k;
+                st4(Ko, K00, K01, K02, K03);
+                st4(Ko + 4, K10, K11, K12, K13);
+            }
+            if (P.io.kff) st2(P.io.kff + i * (2LL * T) + 2 * k, k0, k1);
+        }
+        if (!copy) {
+            Theta<R> tk;
+            tk.eps_dyn = P.ocp.eps_dyn; tk.eps_jac = P.ocp.eps_jac; tk.angle_wrap = P.ocp.angle_wrap;
+            theta_fetch(sTh, lane, tk);
+            theta_fetch_jac(sTh, lane, tk);
+            step_g<R, NOBS>(E, tk, xw, u0, u1, gx, gy);
+        } else {
+            xw.px = N0; xw.py = N1; xw.th = N2; xw.b = N3;
+        }
         if (keep) {
             xn[4 * 32] = u0;
             xn[5 * 32] = u1;
@@ -1081,12 +1118,6 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
         } else {
             st2(P.io.V + i * (2LL * T) + 2 * k, u0, u1);
             st4(P.io.X + i * (4LL * (T + 1)) + 4 * (k + 1), xw.px, xw.py, xw.th, xw.b);
-            if (P.io.K) {
-                R *Ko = P.io.K + i * (8LL * T) + 8 * k;
-                st4(Ko, K00, K01, K02, K03);
-                st4(Ko + 4, K10, K11, K12, K13);
-            }
-            if (P.io.kff) st2(P.io.kff + i * (2LL * T) + 2 * k, k0, k1);
             if (P.write_ref) {
                 R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
                 Ro[EL(k + 1, RR, 0)] = xw.px;

@@ -10,11 +10,6 @@
 #include <cstring>
 #include <mutex>
 
-// 1: line search, selection and commit in one kernel per iteration (fwdc_kernel); 0: the separate fwd / commit kernels
-#ifndef DTMPC_FUSED_COMMIT
-#define DTMPC_FUSED_COMMIT 1
-#endif
-
 #include "dtmpc_math.cuh"
 #include "dtmpc_sens.cuh"
 #include "dtmpc_solve.cuh"
@@ -104,7 +99,7 @@ template <typename R> void convert_io(const dtmpc_solve_io &s, SolveArgs<R> &a) 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Carves the caller's scratch into the solver arrays; with base == nullptr only the size is computed.
-template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int n_alpha, SolveWs<R> *w) {
+template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int /*n_alpha*/, SolveWs<R> *w) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char *p = base ? base + off : nullptr;
@@ -116,18 +111,15 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
     char *l0 = take(nB * sizeof(int)), *l1 = take(nB * sizeof(int));
     char *it = take(nB * sizeof(int)), *flags = take(nB * sizeof(int));
     char *Jcur = take(nB * sizeof(R)), *prev = take(nB * sizeof(R)), *B0 = take(nB * sizeof(R));
-    char *dec = take(nB * sizeof(int)), *keep = take((nB / 32 + 1) * sizeof(unsigned));
     char *traj0 = take(nT * sizeof(R) * (size_t)traj_rows(T)), *traj1 = take(nT * sizeof(R) * (size_t)traj_rows(T));
     char *gains = take(nT * sizeof(R) * (size_t)gain_rows(T));
-    char *ckpt = take(nT * sizeof(R) * CR * (size_t)(MAX_SEG - 1) * (size_t)n_alpha);
     char *ref = take(nT * sizeof(R) * (size_t)ref_rows(T));
     if (w) {
         w->counts = (int *)counts;
         w->list[0] = (int *)l0; w->list[1] = (int *)l1;
         w->it = (int *)it; w->flags = (int *)flags;
-        w->dec = (int *)dec; w->keep = (unsigned *)keep;
         w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0;
-        w->traj[0] = (R *)traj0; w->traj[1] = (R *)traj1; w->gains = (R *)gains; w->ckpt = (R *)ckpt; w->ref = (R *)ref;
+        w->traj[0] = (R *)traj0; w->traj[1] = (R *)traj1; w->gains = (R *)gains; w->ref = (R *)ref;
     }
     return off;
 }
@@ -139,24 +131,9 @@ bool io_ok(const dtmpc_solve_io *s, bool need_ref_or_target) {
     return true;
 }
 
-// One batched OCP: init, max_iter x (Riccati, line search + selection, commit).  Everything is
-// stream-ordered; the host never waits, so all max_iter iterations are enqueued and the ones that find the
-// slots all vacated return at once.
-// candidates rolled out per thread of the line-search kernel (DTMPC_FWD_NC overrides, for tuning)
-[[maybe_unused]] int fwd_candidates_per_thread(int n_eval) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char *e = getenv("DTMPC_FWD_NC");
-        forced = e ? atoi(e) : 0;
-    }
-    // measured on B200 (B = 65,536, T = 50): NC = 1 -> 22.5 ms, NC = 2 -> 26.1 ms, NC = 3 -> 27.8 ms per paper-mode solve:
-    // the interleaved chains do not pay for the lost occupancy, so one candidate per thread stays the default
-    int nc = forced > 0 ? forced : 1;
-    if (nc > 3) nc = 3;
-    if (nc > n_eval) nc = n_eval;
-    return nc < 1 ? 1 : nc;
-}
-
+// One batched OCP: init, then max_iter x (backward Riccati sweep; line search + selection + commit).  Everything is
+// stream-ordered; the host never waits, so all max_iter iterations are enqueued and the ones that find the slots all
+// vacated return at once.
 template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     const long long B = P.B;
     const int T = P.ocp.T;
@@ -165,12 +142,8 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
     for (int c = 0; c < P.ocp.n_alpha; ++c)
         if (P.ocp.alphas[c] != R(0)) P.eval_idx[P.n_eval++] = c;
     for (int c = 0, q = 0; c < P.ocp.n_alpha; ++c) P.eval_pos[c] = P.ocp.alphas[c] != R(0) ? q++ : -1;
-#if DTMPC_FUSED_COMMIT
     P.n_seg = P.n_eval > 0 ? P.n_eval : 1;   // one horizon segment per candidate warp (fwdc_kernel, phase 3)
     if (P.n_seg > T) P.n_seg = T;
-#else
-    P.n_seg = T < MAX_SEG ? T : MAX_SEG;
-#endif
     P.seg_len = (T + P.n_seg - 1) / P.n_seg;
     P.n_seg = (T + P.seg_len - 1) / P.seg_len;
     // kernels with the obstacle count fixed at compile time (1..8 circles, smooth-min; the reference scenario has 5)
@@ -186,10 +159,9 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
 #undef DTMPC_INIT_CASE
     const unsigned gFwd = (unsigned)((B + 31) / 32);
     const unsigned gRic = (unsigned)((B + RIC_BLOCK - 1) / RIC_BLOCK);
-#if DTMPC_FUSED_COMMIT
     const size_t smem = fwdc_smem_bytes(P.n_eval, P.n_seg, sizeof(R));
     const dim3 blk(32, P.n_eval > 0 ? P.n_eval : 1);
-    for (int it = 0; it < P.ocp.max_iter; ++it) {
+    for (int it = 0; it < P.ocp.max_iter; ++it) {   // the last iteration retires every instance still running
         ric_kernel<R><<<gRic, RIC_BLOCK, 0, st>>>(P);
 #define DTMPC_FWDC_LAUNCH(N, U)                                                                          \
     {                                                                                                    \
@@ -214,46 +186,6 @@ template <typename R> int launch_ocp(SolveParams<R> &P, cudaStream_t st) {
         P.parity ^= 1;
     }
     count_launches(1ull + 2ull * (unsigned long long)P.ocp.max_iter);
-#else
-    for (int it = 0; it < P.ocp.max_iter; ++it) {
-        ric_kernel<R><<<gRic, RIC_BLOCK, 0, st>>>(P);
-        {
-            const int nc = fwd_candidates_per_thread(P.n_eval);
-            const int ny = (P.n_eval + nc - 1) / nc;
-            const dim3 blk(32, ny > 0 ? ny : 1);
-            // obstacle counts 1..8 of a smooth-min environment have kernels with the count fixed at compile time
-#define DTMPC_FWD_CASE(N)                                                             \
-    case N:                                                                           \
-        if (P.use_ref) fwd_kernel<R, 1, N, 1><<<gFwd, blk, 0, st>>>(P);               \
-        else fwd_kernel<R, 1, N, 0><<<gFwd, blk, 0, st>>>(P);                         \
-        break;
-            if (nc == 1) {
-                switch (fixed_nobs) {
-                    DTMPC_FWD_CASE(1) DTMPC_FWD_CASE(2) DTMPC_FWD_CASE(3) DTMPC_FWD_CASE(4)
-                    DTMPC_FWD_CASE(5) DTMPC_FWD_CASE(6) DTMPC_FWD_CASE(7) DTMPC_FWD_CASE(8)
-                    default: fwd_kernel<R, 1><<<gFwd, blk, 0, st>>>(P);
-                }
-            }
-#undef DTMPC_FWD_CASE
-            else if (nc == 2) {
-                if (fixed_nobs == 5 && P.use_ref) fwd_kernel<R, 2, 5, 1><<<gFwd, blk, 0, st>>>(P);
-                else if (fixed_nobs == 5) fwd_kernel<R, 2, 5, 0><<<gFwd, blk, 0, st>>>(P);
-                else fwd_kernel<R, 2><<<gFwd, blk, 0, st>>>(P);
-            }
-            else fwd_kernel<R, 3><<<gFwd, blk, 0, st>>>(P);
-        }
-        // the last iteration retires every instance still running
-#define DTMPC_COMMIT_CASE(N) case N: commit_kernel<R, N><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P); break;
-        switch (fixed_nobs) {
-            DTMPC_COMMIT_CASE(1) DTMPC_COMMIT_CASE(2) DTMPC_COMMIT_CASE(3) DTMPC_COMMIT_CASE(4)
-            DTMPC_COMMIT_CASE(5) DTMPC_COMMIT_CASE(6) DTMPC_COMMIT_CASE(7) DTMPC_COMMIT_CASE(8)
-            default: commit_kernel<R><<<gFwd, dim3(32, P.n_seg), 0, st>>>(P);
-        }
-#undef DTMPC_COMMIT_CASE
-        P.parity ^= 1;
-    }
-    count_launches(1ull + 3ull * (unsigned long long)P.ocp.max_iter);
-#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "iLQR kernel launch");
     return DTMPC_OK;

@@ -1,22 +1,21 @@
 // dtmpc_solve.cuh -- batched iLQR (reference core/ddp.py:102-307) as phase-synchronous kernels.
 //
 // The sweep is serial in T and the blocks are tiny (nx = 4, nu = 2): all parallelism is across the batch.  Every iLQR
-// iteration of the whole batch is three launches over the SLOTS that still hold a running instance:
+// iteration of the whole batch is two launches over the SLOTS that still hold a running instance:
 //
 //   ric_kernel     thread per slot                 linearisation (from the stored barrier gradients g_k) + backward
 //                                                  Riccati sweep, register-resident V_x / V_xx, gains K, k
-//   fwd_kernel     thread per (slot, candidate)    forward line search: every alpha != 0 rolls out in its own lane, one
-//                                                  warp per candidate, 32 slots per CTA, so the gains and the current
-//                                                  trajectory are fetched once per CTA (L1) for all candidates; the
-//                                                  candidate costs meet in shared memory and warp 0 takes the decision
-//                                                  (argmin with strict <, tolerance break, trace): nothing but one int
-//                                                  per slot and one ballot per CTA leaves the kernel
-//   commit_kernel  thread per (slot, segment)      rolls the winner out once more (bit-identical to its candidate,
-//                                                  dtmpc_math.cuh), every horizon segment in its own thread from the
-//                                                  state the candidate checkpointed at the segment boundary, and
-//                                                  writes it either into the slot the instance holds in the NEXT
-//                                                  iteration or, if the instance stops here, straight into the
-//                                                  caller's instance-major result tensors
+//   fwdc_kernel    thread per (slot, candidate)    forward line search, selection and commit.  Phase 1: every alpha != 0
+//                                                  rolls out in its own lane, one warp per candidate, 32 slots per CTA,
+//                                                  so the gains and the current trajectory are fetched once per CTA (L1)
+//                                                  for all candidates; the candidate costs meet in shared memory.  Phase
+//                                                  2: warp 0 takes the decision (argmin with strict <, tolerance break,
+//                                                  trace) and reserves the survivors' slots of the next iteration.
+//                                                  Phase 3: the warps roll the winner out once more (bit-identical to
+//                                                  its candidate, dtmpc_math.cuh), one horizon segment each from the
+//                                                  state the candidate checkpointed at the segment boundary, and write
+//                                                  it either into the slot the instance holds in the NEXT iteration or,
+//                                                  if the instance stops here, straight into the caller's result tensors
 //
 // Candidate trajectories are never stored: storing all of them made the line search HBM-bound (2.6 GB per iteration
 // at B = 65,536, profiles/r01b), recomputing the winner costs 1/n_alpha more arithmetic and keeps one trajectory per
@@ -24,15 +23,18 @@
 //
 // Slots, not instances, index the big scratch arrays (trajectory, barrier gradients, gains), and the arrays are
 // tile-major: 32 consecutive slots form a tile whose rows are contiguous, element (step k, row r) of slot s at
-// base[((s/32 * steps + k) * rows + r) * 32 + s%32].  A warp reads one 256 B segment per row, every address of a sweep
-// is one running pointer plus an immediate (a batch-sized row stride cost ~4 integer instructions per load in 64-bit
-// address arithmetic), and the inputs of a step are one contiguous block.  The commit sweep rewrites the whole trajectory every iteration anyway, so it writes it to the
-// instance's next slot (double-buffered), and the next slot is the instance's rank among the survivors: the running
-// instances always occupy slots 0 .. n_act-1 in ascending instance order.  Every access of a warp is then one full
-// contiguous segment however few instances are left, where an index list over instance-indexed arrays cost up to
-// 2.7x the traffic once a third of the batch had converged (profiles/r01c_iterations.txt).  Small per-instance
-// scalars and the tracked reference stay instance-indexed (the reference in the same tile-major form); the
-// order-preserving compaction keeps those gathers monotone.  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
+//     base[((s/32 * steps + k) * rows + r) * 32 + s%32].
+// A warp reads one 256 B segment per row, every address of a sweep is one running pointer plus an immediate (a
+// batch-sized row stride cost ~4 integer instructions per load in 64-bit address arithmetic), and the inputs of a step
+// are one contiguous block.  (Interleaving the rows in PAIRS, so that a lane moves two values per 16-byte access, was
+// measured in round 2: 6 % fewer instructions in the line search, 5 % fewer in the backward sweep -- and a SLOWER step,
+// 14.7 vs 14.1 ms: the 512 B warp accesses hit L1 less often and the aligned register pairs cost spills.)
+// The commit phase rewrites the whole trajectory every iteration
+// anyway, so it writes it to the instance's next slot (double-buffered): the running instances always occupy slots
+// 0 .. n_act-1.  Every access of a warp is then one full contiguous segment however few instances are left, where an
+// index list over instance-indexed arrays cost up to 2.7x the traffic once a third of the batch had converged
+// (profiles/r01c_iterations.txt).  Small per-instance scalars and the tracked reference stay instance-indexed (the
+// reference in the same tile-major form).  Results leave instance-major ([B,T+1,4] ...: one state = one 32 B sector).
 #pragma once
 #include "dtmpc_math.cuh"
 
@@ -50,8 +52,6 @@ template <typename R> struct SolveArgs {
 template <typename R> struct SolveWs {
     int *counts;     // [2] number of occupied slots, per parity
     int *list[2];    // [B] instance held by each slot (ascending), per parity
-    int *dec;        // [B] decision for the slot: bits 0-7 accepted candidate, bit 8 keeps running, bit 9 non-finite
-    unsigned *keep;  // [ceil(B/32)] ballot of 'keeps running' over each group of 32 slots
     int *it;         // [B] completed iterations                         (per instance)
     int *flags;      // [B] bit 0: non-finite in the backward pass       (per instance)
     R *Jcur, *prev, *B0;  // [B] cost of the current trajectory, previous accepted cost, B(h(x0) - tight) (per instance)
@@ -60,7 +60,6 @@ template <typename R> struct SolveWs {
                      // commit); a separate linearisation kernel and its 8 stored jacobian entries per step made the
                      // backward pass HBM-bound (profiles/r01b)
     R *gains;        // [tiles][T][10][32] per slot: K_k (8) then k_k (2)
-    R *ckpt;         // [tiles][n_eval][MAX_SEG-1][5][32] per slot: state of every candidate at the segment boundaries
     R *ref;          // [tiles][T+1][5][32] tracked reference x (3), u (2) of the auxiliary OCP  (per instance)
 };
 
@@ -80,7 +79,6 @@ template <typename R> struct SolveParams {
     int eval_pos[DTMPC_MAX_ALPHAS];  // inverse of eval_idx (-1 for alpha = 0)
     int n_seg, seg_len;              // the commit sweep cuts the horizon into n_seg segments of seg_len steps
 };
-constexpr int MAX_SEG = 5;
 
 constexpr int LS_BLOCK = 128;
 
@@ -97,32 +95,7 @@ __host__ __device__ inline long long tile_off(long long s, long long rows) { ret
 
 template <typename R> struct RefPt { R x0, x1, x2, u0, u1; };
 
-// Bulk asynchronous copy (the TMA engine without a tensor map): one thread moves a contiguous block global -> shared
-// and the bytes are accounted on an mbarrier; consumers wait on the barrier's phase.  PTX ISA 8.x, sm_90+.
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
-    while (!mbar_try_wait(b, parity)) {}
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // UR: -1 = P.use_ref decides at run time, 0 / 1 = fixed at compile time (the line search is instantiated for both)
 template <typename R, int UR = -1>
@@ -225,27 +198,10 @@ __global__ void __launch_bounds__(LS_BLOCK) init_kernel(const __grid_constant__ 
 #ifndef DTMPC_RIC_MAXNREG
 #define DTMPC_RIC_MAXNREG 128
 #endif
-#ifndef DTMPC_RIC_PREFETCH
-#define DTMPC_RIC_PREFETCH 0
-#endif
-// DTMPC_RIC_ASYNC = 1 fetches the inputs of step k-2 with cp.async (LDGSTS: global -> shared without a register in
-// between) into a thread-private ring of RIC_STAGES buffers while step k is computed (every thread reads only what it
-// copied itself, so cp.async.wait_group is the only synchronisation).  Measured on B200 (profiles/r02c, B = 65,536):
-// the sweep alone gains 4 % (126.9 -> 121.7 us, +9 % instructions), but its 27 KB of shared memory per CTA comes out
-// of the L1 the concurrently running line search lives on: the step went from 14.6 to 16.9 ms.  Off.
-#ifndef DTMPC_RIC_ASYNC
-#define DTMPC_RIC_ASYNC 0
-#endif
 #ifndef DTMPC_RIC_BLOCK
 #define DTMPC_RIC_BLOCK 64
 #endif
 constexpr int RIC_BLOCK = DTMPC_RIC_BLOCK;
-constexpr int RIC_STAGES = 4, RIC_AHEAD = 2, RIC_ROWS = 13;
-template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem)), "l"(gmem), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename R>
 __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant__ SolveParams<R> P) {
@@ -286,42 +242,11 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     const R lxx0 = R(2) * th.Q0, lxx1 = R(2) * th.Q1, lxx2 = R(2) * th.Q2, lxx3 = R(2) * th.qb;
     const R luu0 = R(2) * th.R0, luu1 = R(2) * th.R1;
     const R gam = th.gamma, dt = E.dt;
-    // inputs of step k are fetched one step ahead of their use (see fwd_kernel)
     struct RicIn {
         R px, py, pt, pb, u0, u1;
         RefPt<R> r;
         R gx, gy;
     };
-#if DTMPC_RIC_ASYNC
-    __shared__ R sIn[RIC_STAGES][RIC_ROWS][RIC_BLOCK];
-    const bool with_ref = P.use_ref != 0;
-    auto issue = [&](int k, int slot) {   // always commits a group (possibly empty): the group count tracks the steps
-        if (k >= 0) {
-            const R *xk = X + EL(k, TR, 0);
-#pragma unroll
-            for (int r = 0; r < TR; ++r) cp_async_elem<sizeof(R)>(&sIn[slot][r][threadIdx.x], xk + r * 32);
-            if (with_ref) {
-                const R *rk = ref_i + EL(k, RR, 0);
-#pragma unroll
-                for (int r = 0; r < RR; ++r) cp_async_elem<sizeof(R)>(&sIn[slot][TR + r][threadIdx.x], rk + r * 32);
-            }
-        }
-        cp_async_commit();
-    };
-    auto load_step = [&](int slot, RicIn &q) {
-        q.px = sIn[slot][0][threadIdx.x]; q.py = sIn[slot][1][threadIdx.x]; q.pt = sIn[slot][2][threadIdx.x];
-        q.pb = sIn[slot][3][threadIdx.x]; q.u0 = sIn[slot][4][threadIdx.x]; q.u1 = sIn[slot][5][threadIdx.x];
-        q.gx = sIn[slot][6][threadIdx.x]; q.gy = sIn[slot][7][threadIdx.x];
-        if (with_ref) {
-            q.r.x0 = sIn[slot][8][threadIdx.x]; q.r.x1 = sIn[slot][9][threadIdx.x]; q.r.x2 = sIn[slot][10][threadIdx.x];
-            q.r.u0 = sIn[slot][11][threadIdx.x]; q.r.u1 = sIn[slot][12][threadIdx.x];
-        } else {
-            q.r.x0 = t0; q.r.x1 = t1; q.r.x2 = t2; q.r.u0 = R(0); q.r.u1 = R(0);
-        }
-    };
-#pragma unroll
-    for (int a = 0; a < RIC_AHEAD; ++a) issue(T - 1 - a, a);
-#else
     auto load_step = [&](int k, RicIn &q) {
         const R *xk = X + EL(k, TR, 0);
         q.px = xk[0 * 32]; q.py = xk[1 * 32]; q.pt = xk[2 * 32]; q.pb = xk[3 * 32];
@@ -329,31 +254,13 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         ref_at(P, ref_i + EL(k, RR, 0), true, t0, t1, t2, q.r);
         q.gx = xk[6 * 32]; q.gy = xk[7 * 32];
     };
-#endif
     R gnx = X[EL(T, TR, 6)], gny = X[EL(T, TR, 7)];  // g at x_T, then carried backwards
     RicIn in;
-#if DTMPC_RIC_PREFETCH && !DTMPC_RIC_ASYNC
-    load_step(T - 1, in);
-#endif
     int bad_k = -1;   // horizon index at which the backward sweep first produced a non-finite feed-forward gain
-#if DTMPC_RIC_ASYNC
-    int slot = 0;
-#endif
     for (int k = T - 1; k >= 0; --k) {
         RicIn nx;
-#if DTMPC_RIC_ASYNC
-        // the buffer refilled here was read RIC_STAGES - RIC_AHEAD = 2 steps ago
-        issue(k - RIC_AHEAD, (slot + RIC_AHEAD) & (RIC_STAGES - 1));
-        cp_async_wait<RIC_AHEAD>();
-        load_step(slot, in);
-        slot = (slot + 1) & (RIC_STAGES - 1);
-        nx = in;
-#elif DTMPC_RIC_PREFETCH
-        load_step(k > 0 ? k - 1 : 0, nx);
-#else
         load_step(k, in);
         nx = in;
-#endif
         const R px = in.px, py = in.py, pt = in.pt, pb = in.pb, u0 = in.u0, u1 = in.u1;
         const RefPt<R> r = in.r;
         Lin<R> L;
@@ -460,38 +367,16 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// forward line search (core/ddp.py:256-290) and selection (core/ddp.py:293-305).  blockDim = (32, ceil(n_eval / NC)):
-// a CTA covers 32 slots; thread (lane, g) rolls out candidates g*NC .. g*NC+NC-1 of its slot in lockstep.  NC
-// independent dependency chains per thread give the instruction-level parallelism a single fp64 chain lacks (DFMA
-// latency 8.75 cycles, tools/micro), and the gains / trajectory rows of a step are loaded once per thread for its NC
-// candidates.  The costs meet in shared memory; warp 0 picks the winner (strict '<' in list order), applies the
-// tolerance break to the accepted costs and records the decision.
-// ---------------------------------------------------------------------------------------------------------------
 // Register cap of the line search: the kernel needs ~90 registers unconstrained; 72 costs ~60 B of spills per thread
 // but fits 7 CTAs of 4 warps per SM instead of 5.  Same-box sweep (tube step, B = 65,536, full / paper mode):
 // 96: 20.0 / 15.1 ms, 80: 19.7 / 14.4, 76: 19.8 / 14.5, 72: 19.4 / 14.6, 64: 19.5 / 14.5.
 #ifndef DTMPC_FWD_MAXNREG
 #define DTMPC_FWD_MAXNREG 72
 #endif
+
 // The per-instance parameters a rollout step needs (12 values) are the same for every candidate warp of the CTA and
 // constant over the sweep: parked in shared memory and re-read each step they cost 12 LDS instead of ~24 registers.
-#ifndef DTMPC_FWD_SMEM_THETA
-#define DTMPC_FWD_SMEM_THETA 1
-#endif
-// Inputs of a line-search step (x_k, u_k: 6 rows; K_k, k_k: 10 rows of the CTA's tile) staged through a ring of
-// shared-memory buffers by bulk asynchronous copies issued DTMPC_FWD_STAGES steps ahead by one thread; every candidate
-// warp reads them from shared memory.  0: each warp loads them itself (L1 serves the repeats).
-// Measured (B = 65,536, T = 50, same box): staged 14.55 / 18.36 ms, plain loads 14.27 / 18.23 ms per tube solve
-// (paper / full mode; 3, 4 and 6 stages alike): the L1 already serves three of four warps and the per-step barrier
-// traffic costs more than the exposed latency it removes, so the plain path stays the default.
-#ifndef DTMPC_FWD_TMA
-#define DTMPC_FWD_TMA 0
-#endif
-#ifndef DTMPC_FWD_STAGES
-#define DTMPC_FWD_STAGES 4
-#endif
-constexpr int XR = 6;
+
 constexpr int TH_ROWS = 16;
 template <typename R> __device__ __forceinline__ void theta_park(R *s, int lane, const Theta<R> &t) {
     R *v = s + lane;
@@ -511,356 +396,9 @@ template <typename R> __device__ __forceinline__ void theta_fetch_jac(const R *s
 }
 constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 
-template <typename R, int NC, int NOBS = -1, int UR = -1>
-#ifndef DTMPC_FWD2_MAXNREG
-#define DTMPC_FWD2_MAXNREG 168
-#endif
-__global__ void __maxnreg__(NC == 1 ? DTMPC_FWD_MAXNREG : DTMPC_FWD2_MAXNREG) fwd_kernel(const __grid_constant__ SolveParams<R> P) {
-    using m = M<R>;
-    __shared__ R sJ[DTMPC_MAX_ALPHAS * 32];
-    const int n_act = P.ws.counts[P.parity];
-    if ((int)blockIdx.x * 32 >= n_act) return;  // whole CTA
-    const int lane = threadIdx.x;
-    const bool live = (int)blockIdx.x * 32 + lane < n_act;
-    const int j = live ? blockIdx.x * 32 + lane : n_act - 1;  // idle lanes shadow the last slot (they reach the barrier)
-    const long long i = P.ws.list[P.parity][j];
-    const EnvT<R> &E = P.env;
-    const int T = P.ocp.T;
-    int a_idx[NC];
-    R al[NC];
-    bool valid[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) {
-        const int c = threadIdx.y * NC + q;
-        valid[q] = c < P.n_eval;
-        a_idx[q] = P.eval_idx[valid[q] ? c : (P.n_eval > 0 ? P.n_eval - 1 : 0)];  // a padded lane repeats a candidate
-        al[q] = P.ocp.alphas[a_idx[q]];
-    }
-    Theta<R> th;
-    load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
-    R t0 = R(0), t1 = R(0), t2 = R(0);
-    if (UR < 0 ? !P.use_ref : UR == 0) {
-        const R *tp = P.io.target + i * P.io.target_stride;
-        t0 = tp[0]; t1 = tp[1]; t2 = tp[2];
-    }
-    const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
-    const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
-    const R *ref_i = P.ws.ref + tile_off(i, ref_rows(T));
-    R *CK = P.ws.ckpt + tile_off(j, (long long)CR * (MAX_SEG - 1) * P.n_eval);
-
-#if DTMPC_FWD_SMEM_THETA
-    __shared__ R sTh[TH_ROWS * 32];
-    if (threadIdx.y == 0) theta_park(sTh, lane, th);
-    __syncthreads();
-#endif
-
-    State<R> x[NC];
-    R J[NC];
-    {
-        const State<R> x0{X[EL(0, TR, 0)], X[EL(0, TR, 1)], X[EL(0, TR, 2)], X[EL(0, TR, 3)], P.ws.B0[i]};
-#pragma unroll
-        for (int q = 0; q < NC; ++q) {
-            x[q] = x0;
-            J[q] = R(0);
-        }
-    }
-    int k_ck = P.seg_len, seg = 0;  // next segment boundary
-    const R *xp = X, *gp = GK, *rp = ref_i;
-#if DTMPC_FWD_TMA
-    constexpr int ST = DTMPC_FWD_STAGES;
-    constexpr unsigned X_BYTES = XR * 32 * sizeof(R), G_BYTES = GR * 32 * sizeof(R);
-    __shared__ __align__(128) R sIn[ST][(XR + GR) * 32];
-    __shared__ __align__(8) unsigned long long sFull[ST], sEmpty[ST];
-    const bool producer = threadIdx.x == 0 && threadIdx.y == 0;
-    const R *tX = P.ws.traj[P.parity] + (long long)blockIdx.x * traj_rows(T) * 32;   // this CTA's tile
-    const R *tG = P.ws.gains + (long long)blockIdx.x * gain_rows(T) * 32;
-    auto issue = [&](int kk) {
-        const int s = kk % ST;
-        mbar_expect_tx(&sFull[s], X_BYTES + G_BYTES);
-        bulk_g2s(&sIn[s][0], tX + (long long)kk * TR * 32, X_BYTES, &sFull[s]);
-        bulk_g2s(&sIn[s][XR * 32], tG + (long long)kk * GR * 32, G_BYTES, &sFull[s]);
-    };
-    if (producer) {
-        for (int s = 0; s < ST; ++s) {
-            mbar_init(&sFull[s], 1);
-            mbar_init(&sEmpty[s], blockDim.y);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (producer)
-        for (int kk = 0; kk < ST && kk < T; ++kk) issue(kk);
-#endif
-    for (int k = 0; k < T; ++k) {
-        if (k == k_ck) {  // the commit sweep restarts the winner from here (uniform branch)
-            if (live) {
-#pragma unroll
-                for (int q = 0; q < NC; ++q) {
-                    if (!valid[q]) continue;
-                    R *c = CK + EL((threadIdx.y * NC + q) * (MAX_SEG - 1) + seg, CR, 0);
-                    c[0 * 32] = x[q].px; c[1 * 32] = x[q].py; c[2 * 32] = x[q].th; c[3 * 32] = x[q].b; c[4 * 32] = x[q].Bc;
-                }
-            }
-            k_ck += P.seg_len;
-            ++seg;
-        }
-#if DTMPC_FWD_TMA
-        const int st = k % ST;
-        mbar_wait(&sFull[st], (unsigned)(k / ST) & 1u);
-        const R *q = &sIn[st][lane];
-        const R X0 = q[0 * 32], X1 = q[1 * 32], X2 = q[2 * 32], X3 = q[3 * 32];
-        const R v0 = q[4 * 32], v1 = q[5 * 32];
-        const R K00 = q[6 * 32], K01 = q[7 * 32], K02 = q[8 * 32], K03 = q[9 * 32];
-        const R K10 = q[10 * 32], K11 = q[11 * 32], K12 = q[12 * 32], K13 = q[13 * 32];
-        const R k0 = q[14 * 32], k1 = q[15 * 32];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sEmpty[st]);   // this warp is done with the buffer
-        if (producer && k >= 1 && k - 1 + ST < T) {   // refill the buffer every warp released one step ago
-            mbar_wait(&sEmpty[(k - 1) % ST], (unsigned)((k - 1) / ST) & 1u);
-            issue(k - 1 + ST);
-        }
-#else
-        const R X0 = xp[0 * 32], X1 = xp[1 * 32], X2 = xp[2 * 32], X3 = xp[3 * 32];
-        const R v0 = xp[4 * 32], v1 = xp[5 * 32];
-        const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
-        const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
-        const R k0 = gp[8 * 32], k1 = gp[9 * 32];
-#endif
-        RefPt<R> r;
-        ref_at<R, UR>(P, rp, true, t0, t1, t2, r);
-        xp += TR * 32;  // one running pointer per stream: every load is pointer + immediate
-        gp += GR * 32;
-        rp += RR * 32;
-#if DTMPC_FWD_SMEM_THETA
-        Theta<R> tk;
-        tk.eps_dyn = P.ocp.eps_dyn; tk.angle_wrap = P.ocp.angle_wrap;
-        theta_fetch(sTh, lane, tk);
-#else
-        const Theta<R> &tk = th;
-#endif
-        R u0[NC], u1[NC];
-#pragma unroll
-        for (int q = 0; q < NC; ++q) {
-            // du = k + K (x - X_k);  u = clamp(V_k + alpha du)   (core/ddp.py:267-271)
-            const R d0 = x[q].px - X0, d1 = x[q].py - X1, d2 = x[q].th - X2, d3 = x[q].b - X3;
-            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
-            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-            u0[q] = m::fma_(al[q], du0, v0);
-            u1[q] = m::fma_(al[q], du1, v1);
-            clamp_u(E, u0[q], u1[q]);
-            J[q] += stage_cost(tk, x[q].px, x[q].py, x[q].th, x[q].b, u0[q], u1[q], r.x0, r.x1, r.x2, r.u0, r.u1);
-        }
-        step_multi<R, NC, NOBS>(E, tk, x, u0, u1);
-    }
-    RefPt<R> r;
-    ref_at<R, UR>(P, rp, false, t0, t1, t2, r);
-#pragma unroll
-    for (int q = 0; q < NC; ++q) {
-        J[q] += terminal_cost(th, x[q].px, x[q].py, x[q].th, x[q].b, r.x0, r.x1, r.x2);
-        if (valid[q]) sJ[a_idx[q] * 32 + lane] = J[q];
-    }
-    __syncthreads();
-    if (threadIdx.y != 0) return;
-
-    // selection: strict '<' in list order, tolerance break on the accepted costs (core/ddp.py:293-305)
-    bool keep = false;
-    if (live) {
-        const OcpT<R> &o = P.ocp;
-        const R Jc = P.ws.Jcur[i];
-        bool bad = (P.ws.flags[i] & 1) != 0;
-        int best_c = -1;
-        R best = R(0), second = m::inf_();
-        for (int c = 0; c < o.n_alpha; ++c) {
-            const R v = (o.alphas[c] == R(0)) ? Jc : sJ[c * 32 + lane];
-            bad |= !finite_(v);
-            if (best_c < 0 || v < best) {
-                if (best_c >= 0) second = m::min_(second, best);
-                best = v;
-                best_c = c;
-            } else {
-                second = m::min_(second, v);
-            }
-        }
-        int it = P.ws.it[i];
-        bool done = true;
-        if (!bad) {
-            if (o.alphas[best_c] != R(0)) P.ws.Jcur[i] = best;
-            if (P.io.alpha_idx) P.io.alpha_idx[i * o.max_iter + it] = best_c;
-            if (P.io.costs) P.io.costs[i * o.max_iter + it] = best;
-            if (P.io.margins) P.io.margins[i * o.max_iter + it] = second - best;
-            const bool conv = it > 0 && (m::abs_(P.ws.prev[i] - best) < o.tol);
-            P.ws.prev[i] = best;
-            ++it;
-            P.ws.it[i] = it;
-            done = conv || it >= o.max_iter;
-        } else {
-            P.io.status[i] |= DTMPC_ST_NONFINITE << P.status_shift;
-            if (P.io.fail_at && P.io.fail_at[2 * i] < 0) {   // a cost was non-finite (the backward pass reports itself)
-                P.io.fail_at[2 * i] = it;
-                P.io.fail_at[2 * i + 1] = -1;
-            }
-        }
-        keep = !done;
-        P.ws.dec[j] = best_c | (keep ? DEC_KEEP : 0) | (bad ? DEC_BAD : 0);
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) P.ws.keep[blockIdx.x] = mask;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// commit sweep, blockDim = (32, n_seg).  The accepted candidate is rolled out once more, each horizon segment by its
-// own thread: one chain of T steps per instance is a single wave of 14 warps per SM at B = 65,536 and costs the
-// latency of that chain whatever the batch, n_seg chains of T/n_seg steps fill the machine.  A segment starts from
-// the state its candidate checkpointed in fwd_kernel, so it repeats the candidate's operations exactly.  When alpha = 0
-// wins, or a value was non-finite, the current trajectory is kept: those lanes copy it.  An instance that keeps
-// running gets the slot equal to its rank among the running instances (prefix sum over the ballots fwd_kernel left),
-// in the other trajectory buffer; an instance that stops writes the caller's X, V (and K, k of its last backward
-// pass, core/ddp.py:307) and, for the nominal OCP of a tube solve, the reference the auxiliary OCP tracks.
-// ---------------------------------------------------------------------------------------------------------------
-#ifndef DTMPC_SEL_MAXNREG
-#define DTMPC_SEL_MAXNREG 96
-#endif
-#ifndef DTMPC_SEL_SMEM_THETA
-#define DTMPC_SEL_SMEM_THETA 0  // measured neutral for the commit sweep (18.22 vs 18.21 ms)
-#endif
-
-template <typename R, int NOBS = -1>
-__global__ void __maxnreg__(DTMPC_SEL_MAXNREG) commit_kernel(const __grid_constant__ SolveParams<R> P) {
-    using m = M<R>;
-    __shared__ int s_part[MAX_SEG];
-    const int n_act = P.ws.counts[P.parity];
-    if ((int)blockIdx.x * 32 >= n_act) {  // whole CTA
-        if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) P.ws.counts[P.parity ^ 1] = 0;
-        return;
-    }
-    const int lane = threadIdx.x, seg = threadIdx.y;
-    const int j = blockIdx.x * 32 + lane;
-    const bool live = j < n_act;
-    const long long i = live ? P.ws.list[P.parity][j] : 0;
-    Theta<R> th;
-    if (live) load_theta(th, P.io.theta + i * P.io.theta_stride, P.ocp);
-#if DTMPC_SEL_SMEM_THETA
-    __shared__ R sTh[TH_ROWS * 32];
-    if (live && seg == 0) theta_park(sTh, lane, th);  // visible after the barrier below
-#endif
-    // rank of this CTA's first slot among the running instances
-    int acc = 0;
-    for (int w = seg * 32 + lane; w < (int)blockIdx.x; w += 32 * blockDim.y) acc += __popc(P.ws.keep[w]);
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) s_part[seg] = acc;
-    __syncthreads();
-    if (!live) return;
-    int base = 0;
-    for (int q = 0; q < (int)blockDim.y; ++q) base += s_part[q];
-    const unsigned mine = P.ws.keep[blockIdx.x];
-    if (j == n_act - 1 && seg == 0) P.ws.counts[P.parity ^ 1] = base + __popc(mine);  // ballots are clear beyond n_act
-
-    const int d = P.ws.dec[j];
-    const bool keep = (d & DEC_KEEP) != 0;
-    const long long jn = base + __popc(mine & ((1u << lane) - 1u));
-    if (keep && seg == 0) P.ws.list[P.parity ^ 1][jn] = (int)i;
-    const R al = (d & DEC_BAD) ? R(0) : P.ocp.alphas[d & 0xff];
-    const bool copy = al == R(0);  // the current trajectory stays
-
-    const EnvT<R> &E = P.env;
-    const int T = P.ocp.T;
-    const int k_lo = seg * P.seg_len, k_hi = min(T, k_lo + P.seg_len);
-    const R *X = P.ws.traj[P.parity] + tile_off(j, traj_rows(T));
-    const R *GK = P.ws.gains + tile_off(j, gain_rows(T));
-    // destinations: next slot (running) or the result tensors (stopping)
-    R *Xn = P.ws.traj[P.parity ^ 1] + tile_off(jn, traj_rows(T));
-    // (the result pointers of a stopping instance are formed where they are used: held across the sweep they cost
-    // ten registers of every lane for the benefit of the few that stop)
-
-    // state at the head of the segment: x_0, or the winner's checkpoint; and the old trajectory's state there
-    R X0 = X[EL(k_lo, TR, 0)], X1 = X[EL(k_lo, TR, 1)], X2 = X[EL(k_lo, TR, 2)], X3 = X[EL(k_lo, TR, 3)];
-    State<R> x{X0, X1, X2, X3, R(0)};
-    if (seg == 0) {
-        x.Bc = P.ws.B0[i];
-        if (keep) {
-            Xn[EL(0, TR, 0)] = X0; Xn[EL(0, TR, 1)] = X1; Xn[EL(0, TR, 2)] = X2; Xn[EL(0, TR, 3)] = X3;
-            Xn[EL(0, TR, 6)] = X[EL(0, TR, 6)]; Xn[EL(0, TR, 7)] = X[EL(0, TR, 7)];
-        } else {
-            st4(P.io.X + i * (4LL * (T + 1)), X0, X1, X2, X3);
-            if (P.write_ref) {
-                R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
-                Ro[EL(0, RR, 0)] = X0; Ro[EL(0, RR, 1)] = X1; Ro[EL(0, RR, 2)] = X2;
-            }
-            if (P.io.iters) P.io.iters[i] = P.ws.it[i];
-        }
-    } else if (!copy) {
-        const R *c = P.ws.ckpt + tile_off(j, (long long)CR * (MAX_SEG - 1) * P.n_eval) +
-                     EL(P.eval_pos[d & 0xff] * (MAX_SEG - 1) + (seg - 1), CR, 0);
-        x.px = c[0 * 32]; x.py = c[1 * 32]; x.th = c[2 * 32]; x.b = c[3 * 32]; x.Bc = c[4 * 32];
-    }
-    const R *xp = X + EL(k_lo, TR, 0), *gp = GK + EL(k_lo, GR, 0);
-    R *xn = Xn + EL(k_lo, TR, 0);
-    for (int k = k_lo; k < k_hi; ++k) {
-        const R v0 = xp[4 * 32], v1 = xp[5 * 32];
-        const R K00 = gp[0 * 32], K01 = gp[1 * 32], K02 = gp[2 * 32], K03 = gp[3 * 32];
-        const R K10 = gp[4 * 32], K11 = gp[5 * 32], K12 = gp[6 * 32], K13 = gp[7 * 32];
-        const R k0 = gp[8 * 32], k1 = gp[9 * 32];
-        const R N0 = xp[(TR + 0) * 32], N1 = xp[(TR + 1) * 32];
-        const R N2 = xp[(TR + 2) * 32], N3 = xp[(TR + 3) * 32];
-        R u0 = v0, u1 = v1, gx, gy;
-        if (!copy) {
-#if DTMPC_SEL_SMEM_THETA
-            Theta<R> tk;
-            tk.eps_dyn = P.ocp.eps_dyn; tk.eps_jac = P.ocp.eps_jac; tk.angle_wrap = P.ocp.angle_wrap;
-            theta_fetch(sTh, lane, tk);
-            theta_fetch_jac(sTh, lane, tk);
-#else
-            const Theta<R> &tk = th;
-#endif
-            const R d0 = x.px - X0, d1 = x.py - X1, d2 = x.th - X2, d3 = x.b - X3;
-            const R du0 = k0 + m::fma_(K03, d3, m::fma_(K02, d2, m::fma_(K01, d1, K00 * d0)));
-            const R du1 = k1 + m::fma_(K13, d3, m::fma_(K12, d2, m::fma_(K11, d1, K10 * d0)));
-            u0 = m::fma_(al, du0, v0);
-            u1 = m::fma_(al, du1, v1);
-            clamp_u(E, u0, u1);
-            step_g<R, NOBS>(E, tk, x, u0, u1, gx, gy);
-        } else {
-            x.px = N0; x.py = N1; x.th = N2; x.b = N3;
-            gx = xp[(TR + 6) * 32];
-            gy = xp[(TR + 7) * 32];
-        }
-        xp += TR * 32;
-        gp += GR * 32;
-        if (keep) {
-            xn[4 * 32] = u0;
-            xn[5 * 32] = u1;
-            xn[(TR + 0) * 32] = x.px;
-            xn[(TR + 1) * 32] = x.py;
-            xn[(TR + 2) * 32] = x.th;
-            xn[(TR + 3) * 32] = x.b;
-            xn[(TR + 6) * 32] = gx;
-            xn[(TR + 7) * 32] = gy;
-            xn += TR * 32;
-        } else {
-            st2(P.io.V + i * (2LL * T) + 2 * k, u0, u1);
-            st4(P.io.X + i * (4LL * (T + 1)) + 4 * (k + 1), x.px, x.py, x.th, x.b);
-            if (P.io.K) {
-                R *Ko = P.io.K + i * (8LL * T) + 8 * k;
-                st4(Ko, K00, K01, K02, K03);
-                st4(Ko + 4, K10, K11, K12, K13);
-            }
-            if (P.io.kff) st2(P.io.kff + i * (2LL * T) + 2 * k, k0, k1);
-            if (P.write_ref) {
-                R *Ro = P.ws.ref + tile_off(i, ref_rows(T));
-                Ro[EL(k + 1, RR, 0)] = x.px;
-                Ro[EL(k + 1, RR, 1)] = x.py;
-                Ro[EL(k + 1, RR, 2)] = x.th;
-                Ro[EL(k, RR, 3)] = u0;
-                Ro[EL(k, RR, 4)] = u1;
-            }
-        }
-        X0 = N0; X1 = N1; X2 = N2; X3 = N3;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Line search + selection + commit in ONE kernel (round 2).  blockDim = (32, n_eval): a CTA owns 32 slots.
-//   phase 1  every warp rolls out one candidate (as fwd_kernel) and leaves its state at the segment boundaries in
+//   phase 1  every warp rolls out one candidate and leaves its state at the segment boundaries in
 //            SHARED memory (n_eval x (n_seg - 1) x 5 rows x 32 lanes);
 //   phase 2  warp 0 takes the decision for its 32 slots and reserves the survivors' slots of the next iteration with
 //            ONE atomicAdd per CTA on the slot counter (the survivors of a CTA stay contiguous and in order; CTAs land

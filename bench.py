@@ -122,13 +122,9 @@ def executed_work(counters, T, tiles, ocps, n_sens):
     for key in ("fp64_inst", "inst", "dram_bytes"):
         c = lambda f: pu.get(f, {}).get(key, 0.0)
         v = 0.0
-        for n_eval, tile_iters in ocps:
-            v += tiles * T * c("init")
-            if "fwdc" in pu and "commit" not in pu:
-                v += tile_iters * T * (c("ric") + n_eval * c("fwdc"))
-            else:
-                v += tile_iters * T * (c("ric") + n_eval * c("fwd") + c("commit"))
-        v += n_sens * tiles * T * c("sens")
+        for (n_eval, tile_iters), o in zip(ocps, ("n", "a")):   # nominal, auxiliary (the latter also streams its reference)
+            v += tiles * T * c(f"init_{o}") + tile_iters * T * (c(f"ric_{o}") + n_eval * c(f"fwdc_{o}"))
+        v += tiles * T * (c("sens_a") + (c("sens_n") if n_sens > 1 else 0.0))
         out[key] = v
     return out
 

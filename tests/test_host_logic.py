@@ -160,3 +160,58 @@ def test_operators_refuse_cpu_tensors():
 
     with pytest.raises(ValueError, match="CUDA"):
         BatchedTubeMPC(prob, device="cpu")
+
+
+def test_packed_adapters_reproduce_the_reference_updates():
+    """adaptation.RawAdapter (the packed, in-place, graph-capturable form the closed loop uses) against the closed-loop
+    golden: raw parameters and momentum of theta and theta_bar after every reference step, from the constrained-parameter
+    gradient the kernels produce (raw gradient = constrained gradient x chain factor)."""
+    from differentiable_tube_mpc_b200.adaptation import RawAdapter, chain_factor, constrain
+
+    g = load_golden("closedloop_full")
+    cfg = default_dubins_config()
+    prob = TubeProblem.from_config(cfg, mode="full")
+    ad = cfg["adaptation"]
+    kw = dict(lr=ad["lr_eta"], momentum=ad["momentum"], clip_norm=0.0, project_params=ad["project_params"])
+    t64 = lambda v: torch.tensor(v, dtype=torch.float64)
+    th_a = RawAdapter(t64(list(prob.theta_aux0) + [0.0]), with_tight=False, **kw)
+    th_n = RawAdapter(t64(prob.theta_nom0), with_tight=True, **kw)
+    keep = (th_a.theta, th_n.theta, th_a.raw, th_n.vel)
+    for t in range(g["aux_theta"].shape[1]):
+        assert rel_err(th_a.theta.numpy(), g["aux_theta"][0, t]) < 1e-14, t
+        assert rel_err(th_n.theta.numpy(), g["nom_theta"][0, t]) < 1e-14, t
+        ga_raw = torch.zeros(12, dtype=torch.float64)
+        ga_raw[:11] = t64(g["g_theta_raw"][0, t])
+        gn_raw = t64(g["g_theta_bar_raw"][0, t])
+        # the kernels hand over d/d(constrained); divide the reference's raw gradient by the chain factor to get it
+        ca, cn = chain_factor(th_a.raw, False), chain_factor(th_n.raw, True)
+        th_a.update(torch.where(ca != 0, ga_raw / torch.where(ca != 0, ca, torch.ones_like(ca)), torch.zeros_like(ca)))
+        th_n.update(torch.where(cn != 0, gn_raw / torch.where(cn != 0, cn, torch.ones_like(cn)), torch.zeros_like(cn)))
+    assert keep[0] is th_a.theta and keep[1] is th_n.theta and keep[2] is th_a.raw and keep[3] is th_n.vel   # in place
+    assert torch.equal(th_a.theta, constrain(th_a.raw, False)) and float(th_a.theta[11]) == 0.0
+    # per-group norm clip and projection, on the device tensor (no host round trip): groups R (2 entries) and gamma
+    a = RawAdapter(t64([1, 1, 0, 5, -3, 1, 1, 1, 0.5, 0.2, 0.0, 0.3]), with_tight=True, lr=1.0, clip_norm=5.0, project_params=True)
+    g12 = torch.zeros(12, dtype=torch.float64)
+    g12[3:5] = t64([300.0, 400.0]) / chain_factor(a.raw, True)[3:5]
+    a.update(g12)
+    assert torch.allclose(a.raw[3:5], t64([2.0, 1e-4])) and torch.equal(a.raw[0:3], t64([1, 1, 0]))
+
+
+def test_executed_work_model_reads_the_committed_counters():
+    """bench.py's executed-work roofline: the committed ncu counters (profiles/r02_step_counters.json) times the launches
+    a step ran reproduce the step totals they were reduced from (same batch, same iteration counts)."""
+    import json
+    import os
+
+    import bench
+
+    c = bench.load_counters()
+    assert c is not None and {"init_n", "ric_n", "fwdc_n", "ric_a", "fwdc_a", "sens_a", "sens_n"} <= set(c["per_tile_step"])
+    rows = [r for r in open(os.path.join(os.path.dirname(bench.COUNTERS), "r02e_step_launches_full_B65536.csv")) if r.startswith('"')]
+    assert len(rows) > 100
+    # iterations of that profiled step: full mode, 4 evaluated step sizes per OCP; nominal 9.918 / auxiliary 14.714 per solve
+    tiles, T, B = (c["batch"] + 31) // 32, c["horizon"], c["batch"]
+    ex = bench.executed_work(c, T, tiles, [(4, 9.917648 * B / 32), (4, 14.714111 * B / 32)], 2)
+    for k in ("fp64_inst", "inst", "dram_bytes"):
+        assert abs(ex[k] - c["step_totals"][k]) < 0.06 * c["step_totals"][k], (k, ex[k], c["step_totals"][k])
+    assert 50e3 < c["per_solve"]["fp64_inst"] < 65e3 and 0.6e6 < c["per_solve"]["dram_bytes"] < 0.9e6

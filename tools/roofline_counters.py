@@ -49,19 +49,33 @@ for d in launches.values():
     e["time_us"] += d.get("gpu__time_duration.sum", 0.0) / 1e3
     if e["first"] is None:
         e["first"] = d
+for e in fam.values():
+    e.pop("first")
+# per-unit constants from the launches that ran with every instance active: the first ric / fwdc launch after each
+# init_kernel (first init = nominal OCP, second = auxiliary OCP, which also streams the tracked reference) and the
+# sensitivity launches in order (auxiliary, then nominal)
 per_unit = {}
-for f, e in fam.items():
-    d = e.pop("first")
-    if f not in ("init", "ric", "fwd", "commit", "fwdc", "sens"):
+ocp, n_sens = None, 0
+for d in launches.values():
+    f = family(d["name"])
+    if f == "init":
+        ocp = "n" if ocp is None else "a"
+    key = None
+    if f in ("init", "ric", "fwd", "commit", "fwdc") and ocp is not None:
+        key = f"{f}_{ocp}"
+    elif f == "sens":
+        key = "sens_a" if n_sens == 0 else "sens_n"
+        n_sens += 1
+    if key is None or key in per_unit:
         continue
     units = tiles * a.horizon
     if f in ("fwd", "fwdc"):
         m = re.search(r"\((\d+), (\d+), 1\)", d["block"])
         units *= int(m.group(2))                      # one warp per candidate
-    per_unit[f] = {"fp64_inst": d.get("sm__inst_executed_pipe_fp64.sum", 0.0) / units,
-                   "inst": d.get("smsp__inst_executed.sum", 0.0) / units,
-                   "dram_bytes": (d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)) / units,
-                   "time_us_first_launch": d.get("gpu__time_duration.sum", 0.0) / 1e3, "kernel": d["name"].split("(")[0]}
+    per_unit[key] = {"fp64_inst": d.get("sm__inst_executed_pipe_fp64.sum", 0.0) / units,
+                     "inst": d.get("smsp__inst_executed.sum", 0.0) / units,
+                     "dram_bytes": (d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)) / units,
+                     "time_us_first_launch": d.get("gpu__time_duration.sum", 0.0) / 1e3, "kernel": d["name"].split("(")[0]}
 tot = {k: sum(e[k] for e in fam.values()) for k in ("inst", "fp64_inst", "dram_bytes", "time_us")}
 out = {"source": os.path.basename(a.csv), "note": a.note, "batch": a.batch, "horizon": a.horizon, "n_launches": len(launches),
        "step_totals": tot, "per_solve": {k: v / a.batch for k, v in tot.items()}, "families": fam,

@@ -39,6 +39,7 @@ BATCH_PER_GPU = 65536
 NOMINAL_BATCH = 4096
 SEED = 2024
 COUNTERS = os.path.join(ROOT, "profiles", "r02_step_counters.json")
+COUNTERS_F32 = os.path.join(ROOT, "profiles", "r02_step_counters_f32.json")
 
 
 # ---------------------------------------------------------------------------
@@ -105,9 +106,9 @@ def algorithmic_bytes_per_solve(T, full):
     return b
 
 
-def load_counters():
+def load_counters(f32=False):
     try:
-        return json.load(open(COUNTERS))
+        return json.load(open(COUNTERS_F32 if f32 else COUNTERS))
     except Exception:
         return None
 
@@ -503,7 +504,7 @@ def main():
     lo, hi = shard_bounds(total, world, rank)
     prob, w = make_workload(cfg, args.mode, lo, hi, total)
     B, T = hi - lo, args.horizon
-    eng = BatchedTubeMPC(prob, device=dev, dtype=dtype)
+    eng = BatchedTubeMPC(prob, device=dev, dtype=dtype, gains=True)   # every output of the path is written, K and k included
 
     # host (pinned) copies of the step inputs
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).pin_memory()
@@ -682,13 +683,14 @@ def main():
         bytes_solve = algorithmic_bytes_per_solve(T, full) * (1 if is64 else 0.5)
         hbm_ach = bytes_solve * B / (step_ms * 1e-3) / 1e9
         # executed work: fp64-pipe warp instructions (ncu opcode counters of THIS code, profiles/) x what the step ran
-        counters = load_counters() if is64 else None
+        counters = load_counters(f32=not is64)
         ne = lambda o: sum(1 for a in o.ilqr.line_search_alphas if a != 0.0)
         executed = None
         if counters:
             ex = executed_work(counters, T, (B + 31) // 32, [(ne(prob.nominal), it_n / 32.0), (ne(prob.auxiliary), it_a / 32.0)],
                                2 if full else 1)
-            ach_exec = ex["fp64_inst"] * 64.0 / (step_ms * 1e-3) / 1e12      # one fp64-pipe warp instruction = 32 lanes x (1 FMA = 2 flop)
+            # one arithmetic-pipe warp instruction = 32 lanes x (1 FMA = 2 flop); the fp32 counters hold the fp32 pipes
+            ach_exec = ex["fp64_inst"] * 64.0 / (step_ms * 1e-3) / 1e12
             executed = {"fp64_warp_inst_per_solve": ex["fp64_inst"] / B, "issued_warp_inst_per_solve": ex["inst"] / B,
                         "achieved": ach_exec, "frac": ach_exec / peak if peak > 0 else None,
                         "issue_frac": ex["inst"] / (step_ms * 1e-3) / (148 * 4 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6)
@@ -699,7 +701,7 @@ def main():
                                        "frac": ex["dram_bytes"] / (step_ms * 1e-3) / 1e9 / hbm_peak,
                                        "source": "dram__bytes_read+write per launch (ncu, whole batch per launch, cold L2 per "
                                                  "launch) x the launches the step ran; " + os.path.relpath(COUNTERS, ROOT)},
-                        "source": os.path.relpath(COUNTERS, ROOT)}
+                        "source": os.path.relpath(COUNTERS if is64 else COUNTERS_F32, ROOT)}
         frac_exec = executed["frac"] if executed else None
         hbm_frac_act = executed["hbm_actual"]["frac"] if executed else None
         binds = None

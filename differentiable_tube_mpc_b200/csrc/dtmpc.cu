@@ -99,7 +99,7 @@ template <typename R> void convert_io(const dtmpc_solve_io &s, SolveArgs<R> &a) 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Carves the caller's scratch into the solver arrays; with base == nullptr only the size is computed.
-template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int /*n_alpha*/, SolveWs<R> *w) {
+template <typename R> size_t carve_solve_ws(char *base, int T, long long B, [[maybe_unused]] int n_alpha, SolveWs<R> *w) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char *p = base ? base + off : nullptr;
@@ -114,12 +114,20 @@ template <typename R> size_t carve_solve_ws(char *base, int T, long long B, int 
     char *traj0 = take(nT * sizeof(R) * (size_t)traj_rows(T)), *traj1 = take(nT * sizeof(R) * (size_t)traj_rows(T));
     char *gains = take(nT * sizeof(R) * (size_t)gain_rows(T));
     char *ref = take(nT * sizeof(R) * (size_t)ref_rows(T));
+#if DTMPC_CKPT_GLOBAL
+    char *ckpt = take(nT * sizeof(R) * CR * (size_t)(FWDC_MAX_SEG - 1) * (size_t)n_alpha);
+#endif
     if (w) {
         w->counts = (int *)counts;
         w->list[0] = (int *)l0; w->list[1] = (int *)l1;
         w->it = (int *)it; w->flags = (int *)flags;
         w->Jcur = (R *)Jcur; w->prev = (R *)prev; w->B0 = (R *)B0;
         w->traj[0] = (R *)traj0; w->traj[1] = (R *)traj1; w->gains = (R *)gains; w->ref = (R *)ref;
+#if DTMPC_CKPT_GLOBAL
+        w->ckpt = (R *)ckpt;
+#else
+        w->ckpt = nullptr;
+#endif
     }
     return off;
 }

@@ -61,6 +61,7 @@ template <typename R> struct SolveWs {
                      // backward pass HBM-bound (profiles/r01b)
     R *gains;        // [tiles][T][10][32] per slot: K_k (8) then k_k (2)
     R *ref;          // [tiles][T+1][5][32] tracked reference x (3), u (2) of the auxiliary OCP  (per instance)
+    R *ckpt;         // [tiles][n_eval][n_seg-1][5][32] candidate states at the segment boundaries (DTMPC_CKPT_GLOBAL only)
 };
 
 template <typename R> struct SolveParams {
@@ -413,6 +414,11 @@ constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 // the line search.  The number of segments is the number of candidate warps.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FWDC_MAX_SEG = DTMPC_MAX_ALPHAS;
+// 1: the segment checkpoints live in the workspace instead of shared memory (15 KB per CTA in full mode): more of the
+// SM's 256 KB stays L1 for the rows the four candidate warps share
+#ifndef DTMPC_CKPT_GLOBAL
+#define DTMPC_CKPT_GLOBAL 0
+#endif
 
 template <typename R, int NOBS = -1, int UR = -1>
 __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant__ SolveParams<R> P) {
@@ -420,7 +426,13 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *sJ = reinterpret_cast<R *>(smem_raw);                 // [MAX_ALPHAS][32] candidate costs
     R *sTh = sJ + DTMPC_MAX_ALPHAS * 32;                     // [TH_ROWS][32] parked parameters
+#if DTMPC_CKPT_GLOBAL
+    // checkpoints of this CTA's tile in the workspace (written and read back by the same CTA: L2-resident); the lane
+    // offset of the shared-memory form is kept, the tile base differs
+    R *sCk = P.ws.ckpt + (long long)blockIdx.x * ((long long)CR * (FWDC_MAX_SEG - 1) * P.n_eval) * 32;
+#else
     R *sCk = sTh + TH_ROWS * 32;                             // [n_eval][n_seg - 1][CR][32] checkpoints
+#endif
     __shared__ int sDec[32], sJn[32];
     const int n_act = P.ws.counts[P.parity];
     if ((int)blockIdx.x * 32 >= n_act) return;  // whole CTA
@@ -670,7 +682,12 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
 }
 __host__ inline size_t fwdc_smem_bytes(int n_eval, int n_seg, size_t elem) {
     const int ne = n_eval > 0 ? n_eval : 1;
+#if DTMPC_CKPT_GLOBAL
+    (void)ne; (void)n_seg;
+    return elem * 32 * (size_t)(DTMPC_MAX_ALPHAS + TH_ROWS);
+#else
     return elem * 32 * (size_t)(DTMPC_MAX_ALPHAS + TH_ROWS + ne * (n_seg > 1 ? n_seg - 1 : 0) * CR);
+#endif
 }
 
 

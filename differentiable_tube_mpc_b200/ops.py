@@ -96,6 +96,9 @@ _default_ws: Dict[int, Workspace] = {}
 
 
 def default_workspace(device) -> Workspace:
+    """The scratch every operator uses when the caller passes no `workspace`: ONE buffer set per device.  Calls on a
+    device are stream-ordered against each other only if they run on the same stream: callers that drive several streams
+    or host threads on one device must give each its own `Workspace` (as `BatchedTubeMPC` does per engine)."""
     device = torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _default_ws:

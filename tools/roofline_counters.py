@@ -18,6 +18,8 @@ ap.add_argument("--batch", type=int, required=True)
 ap.add_argument("--horizon", type=int, required=True)
 ap.add_argument("--out", required=True)
 ap.add_argument("--note", default="")
+ap.add_argument("--pipe-metric", default="sm__inst_executed_pipe_fp64.sum",
+                help="arithmetic-pipe counter stored as fp64_inst (fp32 runs: sm__inst_executed_pipe_fma.sum)")
 a = ap.parse_args()
 
 rows = list(csv.reader(l for l in open(a.csv) if l.startswith('"')))
@@ -44,7 +46,7 @@ for d in launches.values():
     e = fam.setdefault(f, {"launches": 0, "inst": 0.0, "fp64_inst": 0.0, "dram_bytes": 0.0, "time_us": 0.0, "first": None})
     e["launches"] += 1
     e["inst"] += d.get("smsp__inst_executed.sum", 0.0)
-    e["fp64_inst"] += d.get("sm__inst_executed_pipe_fp64.sum", 0.0)
+    e["fp64_inst"] += d.get(a.pipe_metric, 0.0)
     e["dram_bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     e["time_us"] += d.get("gpu__time_duration.sum", 0.0) / 1e3
     if e["first"] is None:
@@ -72,12 +74,12 @@ for d in launches.values():
     if f in ("fwd", "fwdc"):
         m = re.search(r"\((\d+), (\d+), 1\)", d["block"])
         units *= int(m.group(2))                      # one warp per candidate
-    per_unit[key] = {"fp64_inst": d.get("sm__inst_executed_pipe_fp64.sum", 0.0) / units,
+    per_unit[key] = {"fp64_inst": d.get(a.pipe_metric, 0.0) / units,
                      "inst": d.get("smsp__inst_executed.sum", 0.0) / units,
                      "dram_bytes": (d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)) / units,
                      "time_us_first_launch": d.get("gpu__time_duration.sum", 0.0) / 1e3, "kernel": d["name"].split("(")[0]}
 tot = {k: sum(e[k] for e in fam.values()) for k in ("inst", "fp64_inst", "dram_bytes", "time_us")}
-out = {"source": os.path.basename(a.csv), "note": a.note, "batch": a.batch, "horizon": a.horizon, "n_launches": len(launches),
+out = {"source": os.path.basename(a.csv), "note": a.note, "pipe_metric": a.pipe_metric, "batch": a.batch, "horizon": a.horizon, "n_launches": len(launches),
        "step_totals": tot, "per_solve": {k: v / a.batch for k, v in tot.items()}, "families": fam,
        "per_tile_step": per_unit,
        "unit": "tile-step = 32 instances x 1 horizon step of one launch (line search: per candidate warp)"}

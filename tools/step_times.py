@@ -11,9 +11,10 @@ from differentiable_tube_mpc_b200.engine import BatchedTubeMPC
 ap = argparse.ArgumentParser()
 ap.add_argument("--mode", default="full"); ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--steps", type=int, default=10); ap.add_argument("--horizon", type=int, default=50)
+ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
 a = ap.parse_args()
 cfg = default_dubins_config(); cfg["system"]["horizon_N"] = a.horizon
-dev = torch.device("cuda:0"); dt = torch.float64
+dev = torch.device("cuda:0"); dt = torch.float64 if a.dtype == "f64" else torch.float32
 prob, w = bench.make_workload(cfg, a.mode, 0, a.batch, a.batch)
 eng = BatchedTubeMPC(prob, device=dev, dtype=dt)
 cu = lambda v: torch.as_tensor(np.ascontiguousarray(v), dtype=dt, device=dev)

@@ -414,10 +414,12 @@ constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 // the line search.  The number of segments is the number of candidate warps.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FWDC_MAX_SEG = DTMPC_MAX_ALPHAS;
-// 1: the segment checkpoints live in the workspace instead of shared memory (15 KB per CTA in full mode): more of the
-// SM's 256 KB stays L1 for the rows the four candidate warps share
+// 1: the segment checkpoints live in the workspace instead of shared memory (15 KB per CTA in full mode, 38 KB with six
+// candidates): more of the SM's 256 KB stays L1 for the rows the candidate warps share.  Same-call A/B (B = 65,536,
+// full mode): fwdc 413.8 -> 406.5 us per launch, step 14.06 -> 13.81 ms, +6 % DRAM traffic (the checkpoints of a tile
+// are written and read back by the same CTA, mostly out of L2).
 #ifndef DTMPC_CKPT_GLOBAL
-#define DTMPC_CKPT_GLOBAL 0
+#define DTMPC_CKPT_GLOBAL 1
 #endif
 
 template <typename R, int NOBS = -1, int UR = -1>

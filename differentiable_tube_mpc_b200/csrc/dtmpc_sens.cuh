@@ -248,17 +248,17 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         ENT_V(3, 0) ENT_V(3, 1) ENT_V(3, 2) ENT_V(3, 3)
 #undef ENT_V
         // stash for the forward sweep (row 0: h, rows 1..38 below)
-        WK(1) = K00; WK(2) = K01; WK(3) = K02; WK(4) = K03;
-        WK(5) = K10; WK(6) = K11; WK(7) = K12; WK(8) = K13;
-        WK(9) = k0; WK(10) = k1;
-        WK(11) = Vx0; WK(12) = Vx1; WK(13) = Vx2; WK(14) = Vx3;
-        WK(15) = V00; WK(16) = V01; WK(17) = V02; WK(18) = V03;
-        WK(19) = V10; WK(20) = V11; WK(21) = V12; WK(22) = V13;
-        WK(23) = V20; WK(24) = V21; WK(25) = V22; WK(26) = V23;
-        WK(27) = V30; WK(28) = V31; WK(29) = V32; WK(30) = V33;
-        WK(31) = L.a02; WK(32) = L.a12; WK(33) = L.r0; WK(34) = L.r1;
-        WK(35) = L.r2; WK(36) = L.b00; WK(37) = L.b10; WK(38) = L.s0;
-        WK(0) = hk;
+        st_stream(wk + (1) * 32, K00); st_stream(wk + (2) * 32, K01); st_stream(wk + (3) * 32, K02); st_stream(wk + (4) * 32, K03);
+        st_stream(wk + (5) * 32, K10); st_stream(wk + (6) * 32, K11); st_stream(wk + (7) * 32, K12); st_stream(wk + (8) * 32, K13);
+        st_stream(wk + (9) * 32, k0); st_stream(wk + (10) * 32, k1);
+        st_stream(wk + (11) * 32, Vx0); st_stream(wk + (12) * 32, Vx1); st_stream(wk + (13) * 32, Vx2); st_stream(wk + (14) * 32, Vx3);
+        st_stream(wk + (15) * 32, V00); st_stream(wk + (16) * 32, V01); st_stream(wk + (17) * 32, V02); st_stream(wk + (18) * 32, V03);
+        st_stream(wk + (19) * 32, V10); st_stream(wk + (20) * 32, V11); st_stream(wk + (21) * 32, V12); st_stream(wk + (22) * 32, V13);
+        st_stream(wk + (23) * 32, V20); st_stream(wk + (24) * 32, V21); st_stream(wk + (25) * 32, V22); st_stream(wk + (26) * 32, V23);
+        st_stream(wk + (27) * 32, V30); st_stream(wk + (28) * 32, V31); st_stream(wk + (29) * 32, V32); st_stream(wk + (30) * 32, V33);
+        st_stream(wk + (31) * 32, L.a02); st_stream(wk + (32) * 32, L.a12); st_stream(wk + (33) * 32, L.r0); st_stream(wk + (34) * 32, L.r1);
+        st_stream(wk + (35) * 32, L.r2); st_stream(wk + (36) * 32, L.b00); st_stream(wk + (37) * 32, L.b10); st_stream(wk + (38) * 32, L.s0);
+        st_stream(wk + (0) * 32, hk);
     }
 
     // ---- forward sweep (core/ddp.py:412-425) + gradient accumulation ---------
@@ -277,9 +277,9 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
     const R *xrk = xrp, *urk = urp, *Xbk = Xb;
     R *dXk = dXo, *dVk = dVo, *dLk = dLo, *gxk = gxo, *guk = guo;
     for (int k = 0; k < T; ++k) {
-        const R K00 = WK(1), K01 = WK(2), K02 = WK(3), K03 = WK(4);
-        const R K10 = WK(5), K11 = WK(6), K12 = WK(7), K13 = WK(8);
-        const R k0 = WK(9), k1 = WK(10);
+        const R K00 = ld_stream(wk + (1) * 32), K01 = ld_stream(wk + (2) * 32), K02 = ld_stream(wk + (3) * 32), K03 = ld_stream(wk + (4) * 32);
+        const R K10 = ld_stream(wk + (5) * 32), K11 = ld_stream(wk + (6) * 32), K12 = ld_stream(wk + (7) * 32), K13 = ld_stream(wk + (8) * 32);
+        const R k0 = ld_stream(wk + (9) * 32), k1 = ld_stream(wk + (10) * 32);
         R px, py, pt, pb, u0, u1;
         ld4(Xk, px, py, pt, pb);
         ld2(Vk, u0, u1);
@@ -290,15 +290,15 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         if (a0) du0 = R(0);
         if (a1) du1 = R(0);
         // delta_lambda_k = tilde V_x,k + V_xx,k delta_x_k
-        const R l0 = WK(11) + m::fma_(WK(18), d3, m::fma_(WK(17), d2, m::fma_(WK(16), d1, WK(15) * d0)));
-        const R l1 = WK(12) + m::fma_(WK(22), d3, m::fma_(WK(21), d2, m::fma_(WK(20), d1, WK(19) * d0)));
-        const R l2 = WK(13) + m::fma_(WK(26), d3, m::fma_(WK(25), d2, m::fma_(WK(24), d1, WK(23) * d0)));
-        const R l3 = WK(14) + m::fma_(WK(30), d3, m::fma_(WK(29), d2, m::fma_(WK(28), d1, WK(27) * d0)));
+        const R l0 = ld_stream(wk + (11) * 32) + m::fma_(ld_stream(wk + (18) * 32), d3, m::fma_(ld_stream(wk + (17) * 32), d2, m::fma_(ld_stream(wk + (16) * 32), d1, ld_stream(wk + (15) * 32) * d0)));
+        const R l1 = ld_stream(wk + (12) * 32) + m::fma_(ld_stream(wk + (22) * 32), d3, m::fma_(ld_stream(wk + (21) * 32), d2, m::fma_(ld_stream(wk + (20) * 32), d1, ld_stream(wk + (19) * 32) * d0)));
+        const R l2 = ld_stream(wk + (13) * 32) + m::fma_(ld_stream(wk + (26) * 32), d3, m::fma_(ld_stream(wk + (25) * 32), d2, m::fma_(ld_stream(wk + (24) * 32), d1, ld_stream(wk + (23) * 32) * d0)));
+        const R l3 = ld_stream(wk + (14) * 32) + m::fma_(ld_stream(wk + (30) * 32), d3, m::fma_(ld_stream(wk + (29) * 32), d2, m::fma_(ld_stream(wk + (28) * 32), d1, ld_stream(wk + (27) * 32) * d0)));
         st4(dXk, d0, d1, d2, d3);
         st2(dVk, du0, du1);
         st4(dLk, l0, l1, l2, l3);
         bad |= !finite_((l0 + l1) + (l2 + l3) + (du0 + du1));
-        const R hk = WK(0);
+        const R hk = ld_stream(wk + (0) * 32);
         R r0, r1, r2, q0, q1;
         if (xrp) {
             r0 = xrk[0]; r1 = xrk[1]; r2 = xrk[2];
@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant_
         p_r0 = r0; p_r1 = r1; p_r2 = r2; p_q0 = q0; p_q1 = q1;
         p_d0 = d0; p_d1 = d1; p_d2 = d2; p_d3 = d3; p_du0 = du0; p_du1 = du1; p_h = hk;
         // delta_x_{k+1} = A delta_x_k + B delta_u_k
-        const R a02 = WK(31), a12 = WK(32), R0 = WK(33), R1 = WK(34), R2 = WK(35);
-        const R b00 = WK(36), b10 = WK(37), s0 = WK(38);
+        const R a02 = ld_stream(wk + (31) * 32), a12 = ld_stream(wk + (32) * 32), R0 = ld_stream(wk + (33) * 32), R1 = ld_stream(wk + (34) * 32), R2 = ld_stream(wk + (35) * 32);
+        const R b00 = ld_stream(wk + (36) * 32), b10 = ld_stream(wk + (37) * 32), s0 = ld_stream(wk + (38) * 32);
         const R n0 = m::fma_(b00, du0, m::fma_(a02, d2, d0));
         const R n1 = m::fma_(b10, du0, m::fma_(a12, d2, d1));
         const R n2 = m::fma_(dt, du1, d2);

@@ -250,10 +250,16 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
     };
     auto load_step = [&](int k, RicIn &q) {
         const R *xk = X + EL(k, TR, 0);
-        q.px = xk[0 * 32]; q.py = xk[1 * 32]; q.pt = xk[2 * 32]; q.pb = xk[3 * 32];
-        q.u0 = xk[4 * 32]; q.u1 = xk[5 * 32];
-        ref_at(P, ref_i + EL(k, RR, 0), true, t0, t1, t2, q.r);
-        q.gx = xk[6 * 32]; q.gy = xk[7 * 32];
+        q.px = ld_stream(xk + 0 * 32); q.py = ld_stream(xk + 1 * 32); q.pt = ld_stream(xk + 2 * 32);
+        q.pb = ld_stream(xk + 3 * 32); q.u0 = ld_stream(xk + 4 * 32); q.u1 = ld_stream(xk + 5 * 32);
+        if (P.use_ref) {
+            const R *rk = ref_i + EL(k, RR, 0);
+            q.r.x0 = ld_stream(rk + 0 * 32); q.r.x1 = ld_stream(rk + 1 * 32); q.r.x2 = ld_stream(rk + 2 * 32);
+            q.r.u0 = ld_stream(rk + 3 * 32); q.r.u1 = ld_stream(rk + 4 * 32);
+        } else {
+            q.r.x0 = t0; q.r.x1 = t1; q.r.x2 = t2; q.r.u0 = R(0); q.r.u1 = R(0);
+        }
+        q.gx = ld_stream(xk + 6 * 32); q.gy = ld_stream(xk + 7 * 32);
     };
     R gnx = X[EL(T, TR, 6)], gny = X[EL(T, TR, 7)];  // g at x_T, then carried backwards
     RicIn in;
@@ -328,10 +334,10 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
         k0 = -k0; k1 = -k1;
         {
             R *o = GK + EL(k, GR, 0);
-            o[0 * 32] = K00; o[1 * 32] = K01; o[2 * 32] = K02; o[3 * 32] = K03;
-            o[4 * 32] = K10; o[5 * 32] = K11; o[6 * 32] = K12; o[7 * 32] = K13;
-            o[8 * 32] = k0;
-            o[9 * 32] = k1;
+            st_stream(o + 0 * 32, K00); st_stream(o + 1 * 32, K01); st_stream(o + 2 * 32, K02); st_stream(o + 3 * 32, K03);
+            st_stream(o + 4 * 32, K10); st_stream(o + 5 * 32, K11); st_stream(o + 6 * 32, K12); st_stream(o + 7 * 32, K13);
+            st_stream(o + 8 * 32, k0);
+            st_stream(o + 9 * 32, k1);
         }
         if (bad_k < 0 && !finite_(k0 + k1)) bad_k = k;   // the sweep runs backwards: the first hit is where it broke
         // V_x = Q_x + K^T Q_uu k + K^T Q_u + Q_xu k   (un-regularised Q_uu, core/ddp.py:251)
@@ -658,14 +664,14 @@ __global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant
             xw.px = N0; xw.py = N1; xw.th = N2; xw.b = N3;
         }
         if (keep) {
-            xn[4 * 32] = u0;
-            xn[5 * 32] = u1;
-            xn[(TR + 0) * 32] = xw.px;
-            xn[(TR + 1) * 32] = xw.py;
-            xn[(TR + 2) * 32] = xw.th;
-            xn[(TR + 3) * 32] = xw.b;
-            xn[(TR + 6) * 32] = gx;
-            xn[(TR + 7) * 32] = gy;
+            st_stream(xn + 4 * 32, u0);
+            st_stream(xn + 5 * 32, u1);
+            st_stream(xn + (TR + 0) * 32, xw.px);
+            st_stream(xn + (TR + 1) * 32, xw.py);
+            st_stream(xn + (TR + 2) * 32, xw.th);
+            st_stream(xn + (TR + 3) * 32, xw.b);
+            st_stream(xn + (TR + 6) * 32, gx);
+            st_stream(xn + (TR + 7) * 32, gy);
             xn += TR * 32;
         } else {
             st2(P.io.V + i * (2LL * T) + 2 * k, u0, u1);

@@ -87,8 +87,11 @@ template <typename R> __device__ __forceinline__ void store_grads(R *out, const 
 }
 
 // NOBS > 0: obstacle count of a smooth-min environment fixed at compile time (as in the solver kernels)
+#ifndef DTMPC_SENS_MAXNREG
+#define DTMPC_SENS_MAXNREG 255
+#endif
 template <typename R, int NOBS = -1>
-__global__ void __launch_bounds__(SENS_BLOCK) sens_kernel(const __grid_constant__ SensParams<R> P) {
+__global__ void __maxnreg__(DTMPC_SENS_MAXNREG) sens_kernel(const __grid_constant__ SensParams<R> P) {
     using m = M<R>;
     const long long i = (long long)blockIdx.x * SENS_BLOCK + threadIdx.x;
     if (i >= P.B) return;

@@ -207,7 +207,7 @@ def test_executed_work_model_reads_the_committed_counters():
 
     c = bench.load_counters()
     assert c is not None and {"init_n", "ric_n", "fwdc_n", "ric_a", "fwdc_a", "sens_a", "sens_n"} <= set(c["per_tile_step"])
-    rows = [r for r in open(os.path.join(os.path.dirname(bench.COUNTERS), "r02e_step_launches_full_B65536.csv")) if r.startswith('"')]
+    rows = [r for r in open(os.path.join(os.path.dirname(bench.COUNTERS), "r02m_step_launches_full_B65536.csv")) if r.startswith('"')]
     assert len(rows) > 100
     # iterations of that profiled step: full mode, 4 evaluated step sizes per OCP; nominal 9.918 / auxiliary 14.714 per solve
     tiles, T, B = (c["batch"] + 31) // 32, c["horizon"], c["batch"]

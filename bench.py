@@ -778,7 +778,7 @@ def sweep_point(cfg, dev, mode, T, B, dtype_name, steps=4):
     res = {"T": T, "B": B, "dtype": dtype_name, "mode": mode, "value": B * steps / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms / steps, "steps": steps, "iters_per_solve": float((out.nominal.iters.sum() + out.auxiliary.iters.sum()) / B),
            "nonfinite": int((out.status != 0).sum()), "launch": "cuda_graph_replay, one step in flight"}
-    counters = load_counters() if dtype_name == "f64" else None
+    counters = load_counters(f32=dtype_name != "f64")
     if counters:
         ne = lambda o: sum(1 for a in o.ilqr.line_search_alphas if a != 0.0)
         ex = executed_work(counters, T, (B + 31) // 32, [(ne(prob.nominal), float(out.nominal.iters.sum()) / 32.0),

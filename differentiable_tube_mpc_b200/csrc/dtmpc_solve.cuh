@@ -405,8 +405,8 @@ constexpr int DEC_KEEP = 1 << 8, DEC_BAD = 1 << 9;
 
 // ---------------------------------------------------------------------------------------------------------------
 // Line search + selection + commit in ONE kernel (round 2).  blockDim = (32, n_eval): a CTA owns 32 slots.
-//   phase 1  every warp rolls out one candidate and leaves its state at the segment boundaries in
-//            SHARED memory (n_eval x (n_seg - 1) x 5 rows x 32 lanes);
+//   phase 1  every warp rolls out one candidate and leaves its state at the segment boundaries in the CTA's
+//            checkpoint tile (n_eval x (n_seg - 1) x 5 rows x 32 lanes; in the workspace, see DTMPC_CKPT_GLOBAL);
 //   phase 2  warp 0 takes the decision for its 32 slots and reserves the survivors' slots of the next iteration with
 //            ONE atomicAdd per CTA on the slot counter (the survivors of a CTA stay contiguous and in order; CTAs land
 //            in the order they finish.  Results do not depend on which slot an instance occupies: every instance is

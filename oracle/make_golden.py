@@ -490,6 +490,9 @@ def main():
         # name: (instances, mode, H)
         "closedloop_paper": ([kat], "paper", 4),
         "closedloop_full": ([kat], "full", 3),
+        # closed loops from random, perturbed starts (KAT-0 above is a chain of roundoff ties; these are not)
+        "closedloop_paper_rand": (random_instances(4, 909, cfg, h_min=0.5), "paper", 6),
+        "closedloop_full_rand": (random_instances(3, 910, cfg, h_min=0.5), "full", 4),
         "random_paper": (random_instances(40, 2024, cfg) + random_instances(16, 77, cfg, vary_weights=True), "paper", 1),
         "random_full": (random_instances(16, 4242, cfg) + random_instances(8, 99, cfg, vary_weights=True), "full", 1),
         "paper_T20": ([dict(i, T=20) for i in random_instances(12, 31337, cfg, vary_weights=True, h_min=0.05)], "paper", 2),

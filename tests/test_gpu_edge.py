@@ -57,11 +57,36 @@ def _check(oracle, prob, env, nom, aux, x0n, x0a, T):
     for i in np.nonzero(same)[0]:
         same[i] &= np.array_equal(want["aidx_n"][i][: want["iters_n"][i]], rn.alpha_idx.cpu().numpy()[i][: want["iters_n"][i]])
         same[i] &= np.array_equal(want["aidx_a"][i][: want["iters_a"][i]], ra.alpha_idx.cpu().numpy()[i][: want["iters_a"][i]])
-    assert same.sum() >= 0.8 * max(1, ok.sum()), (same.sum(), ok.sum())   # the rest are roundoff ties (App. B Q12)
+    # every instance whose decisions differ must be a roundoff tie of the oracle's own (App. B Q12): a line-search margin
+    # or a tolerance test within 1e-10 relative of flipping
+    def tied(i, tag, tol):
+        n = int(want[f"iters_{tag}"][i])
+        c, mg = want[f"costs_{tag}"][i], want[f"marg_{tag}"][i]
+        if not n:
+            return False
+        d = np.abs(np.diff(c[:n]))
+        return bool(np.nanmin(np.abs(mg[:n]) / np.maximum(np.abs(c[:n]), 1e-300)) < 1e-10) or bool(
+            d.size and np.min(np.abs(d - tol)) < 1e-9 * abs(c[0]))
+
+    for i in np.nonzero(ok & ~same)[0]:
+        nom_same = want["iters_n"][i] == rn.iters[i].item() and np.array_equal(
+            want["aidx_n"][i][: want["iters_n"][i]], rn.alpha_idx.cpu().numpy()[i][: want["iters_n"][i]])
+        # a tie-broken nominal solve changes the auxiliary problem's reference, so only the first differing layer is judged
+        assert tied(i, "n", nom.tol) if not nom_same else tied(i, "a", aux.tol), (
+            i, "decision mismatch without a tie in the oracle's own margins")
+    # iterates that left the safe set (barrier costs ~1e16 and above: a full step without a smaller candidate to fall
+    # back on) amplify roundoff without bound in any implementation; they are compared in the median only
+    wild = (np.nan_to_num(want["costs_n"], nan=0.0).max(axis=1) > 1e12) | (np.nan_to_num(want["costs_a"], nan=0.0).max(axis=1) > 1e12)
+    worst = 0.0
     for got, key in ((rn.X, "Xn"), (rn.V, "Un"), (ra.X, "Xa"), (ra.V, "Ua"), (rn.K, "Kn"), (ra.K, "Ka")):
         e = per_instance_rel(got.cpu().numpy()[same], want[key][same], floor=1e-6)
         assert e.size == 0 or np.median(e) < 1e-12, (key, np.median(e))
-        assert e.size == 0 or np.quantile(e, 0.9) < 1e-9, (key, np.quantile(e, 0.9))
+        worst = max(worst, e[~wild[same]].max(initial=0.0))
+    print(f"[edge T={T} B={B}] decisions equal on {int(same.sum())}/{int(ok.sum())}; worst rel err where equal "
+          f"{worst:.1e} ({int((wild & same).sum())} outside the safe set)")
+    assert same.sum() >= 0.95 * max(1, ok.sum()), (same.sum(), ok.sum())     # measured: all, in every case of this file
+    assert (wild & same).sum() <= 0.1 * B
+    assert worst < 1e-9, worst
     # whatever the decisions: the returned trajectory is the rollout of the returned controls, bit for bit
     for r, ocp, th in ((rn, prob.nominal, prob.theta_nom0), (ra, prob.auxiliary, prob.theta_aux0)):
         x0 = cu(x0n if r is rn else x0a)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_golden, make_instances, per_instance_rel, rel_err
+from helpers import golden_step_conditioning, load_golden, make_instances, per_instance_rel, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -241,8 +241,8 @@ def test_tube_solve_sens_grads_vs_oracle(oracle, mode, B, seed):
 # directly against what the reference computed (tests/golden, made by oracle/make_golden.py)
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["closedloop_paper", "random_paper", "paper_T20", "closedloop_full", "random_full",
-                                  "full_gamma"])
-def test_against_reference_goldens(name):
+                                  "full_gamma", "closedloop_paper_rand", "closedloop_full_rand"])
+def test_against_reference_goldens(oracle, name):
     from differentiable_tube_mpc_b200 import ops
 
     g = load_golden(name)
@@ -260,6 +260,7 @@ def test_against_reference_goldens(name):
     good = np.ones(B, dtype=bool)
     tied = np.zeros(B, dtype=bool)
     wild = np.zeros(B, dtype=bool)
+    loose = set()
     for tag, r in (("nom", rn), ("aux", ra)):
         it_w, it_g = flat(f"{tag}_iters"), r.iters.cpu().numpy()
         ai_w, ai_g = flat(f"{tag}_alpha_idx"), r.alpha_idx.cpu().numpy()
@@ -275,15 +276,26 @@ def test_against_reference_goldens(name):
                 tied[i] |= bool(np.min((srt[:, 1] - srt[:, 0]) / np.abs(srt[:, 0])) < 1e-9)
                 wild[i] |= bool(np.nanmax(c) > 1e12)
     assert (good | tied | wild).all(), f"unexplained decision mismatch at {np.nonzero(~(good | tied | wild))[0]}"
-    if B >= 16:
-        assert good.mean() >= 0.85, f"only {good.mean():.0%} of the reference decisions reproduced"
+    # measured share of the reference's decisions reproduced exactly (printed below): all of random_paper (56),
+    # random_full (24), full_gamma (16), closedloop_full_rand (12); 23/24 of paper_T20 and 22/24 of closedloop_paper_rand
+    # (solves among candidates outside the safe set); the KAT-0 closed loops are roundoff-tie chains (0/4, 2/3)
+    floor_ = {"closedloop_paper": 0.0, "closedloop_full": 0.5, "closedloop_paper_rand": 0.9}.get(name, 0.95)
+    assert good.mean() >= floor_, f"only {good.mean():.0%} of the reference decisions reproduced"
     for key, got in (("nom_X", rn.X), ("nom_V", rn.V), ("aux_X", ra.X), ("aux_V", ra.V), ("nom_K", rn.K),
                      ("aux_K", ra.K)):
         e = per_instance_rel(got.cpu().numpy(), flat(key))
         print(f"[golden {name}] {key}: median {np.median(e):.1e} max(decisions equal) {e[good].max(initial=0.0):.1e} "
               f"max(all) {e.max():.1e}; decisions equal on {good.sum()}/{B}")
-        # the fixtures contain a few ill-conditioned instances (reference vs oracle differ by up to 4e-10 there)
-        assert e[good].max(initial=0.0) < 5e-9, (key, e[good].max())
+        # the fixtures contain a few ill-conditioned instances (reference vs oracle differ by up to 4e-10 there); a
+        # solve further off than that must be one the oracle itself cannot hold still under a 1e-14 perturbation
+        for i in np.nonzero(good & (e >= 5e-9))[0]:
+            if int(i) in loose:     # classified by an earlier tensor of the same step (the auxiliary problem tracks
+                continue            # the nominal solution, so it inherits the nominal solve's conditioning)
+            _, moved = golden_step_conditioning(oracle, g, cfg, i // H, i % H, key[:3])
+            print(f"[golden {name}] {key} solve {i}: off by {e[i]:.1e}, the oracle moves {moved:.1e} under 1e-14")
+            assert e[i] < 100.0 * moved, (key, i, e[i], moved)
+            loose.add(int(i))
+        assert len(loose) <= max(1, B // 20), loose
         if good.any():
             assert np.median(e[good]) < 1e-12, (key, np.median(e[good]))
         if key.endswith(("_X", "_V")):

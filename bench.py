@@ -723,11 +723,6 @@ def main():
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                             "bytes_per_solve": bytes_solve, "basis": "algorithmic (compulsory) bytes"}}
-        if extras and is64:
-            for pt in extras.get("cfg4_sweep", []):
-                if "fp64_tflops_executed" in pt and peak > 0:
-                    pt["fp64_frac_executed"] = pt["fp64_tflops_executed"] / peak
-                    pt["hbm_frac_from_counters"] = pt["dram_gbs_from_counters"] / hbm_peak
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_sample or cores * (1280 if full else 2048)  # ~10-20 s of CPU work
@@ -784,8 +779,16 @@ def sweep_point(cfg, dev, mode, T, B, dtype_name, steps=4):
         ex = executed_work(counters, T, (B + 31) // 32, [(ne(prob.nominal), float(out.nominal.iters.sum()) / 32.0),
                                                         (ne(prob.auxiliary), float(out.auxiliary.iters.sum()) / 32.0)],
                            2 if mode == "full" else 1)
-        res["fp64_tflops_executed"] = ex["fp64_inst"] * 64.0 / (ms / steps * 1e-3) / 1e12
+        # the arithmetic pipe of this dtype (fp64: DFMA/DADD/DMUL pipe; fp32: FMA pipe) against ITS peak, measured here
+        from differentiable_tube_mpc_b200 import ops
+        f64 = dtype_name == "f64"
+        pipe_peak = ops.measure_fp64_peak_tflops() if f64 else ops.measure_fp32_peak_tflops()
+        res["pipe"] = "fp64" if f64 else "fp32 fma"
+        res["pipe_tflops_executed"] = ex["fp64_inst"] * 64.0 / (ms / steps * 1e-3) / 1e12
+        res["pipe_peak_tflops"] = pipe_peak
+        res["pipe_frac_executed"] = res["pipe_tflops_executed"] / pipe_peak if pipe_peak > 0 else None
         res["dram_gbs_from_counters"] = ex["dram_bytes"] / (ms / steps * 1e-3) / 1e9
+        res["hbm_frac_from_counters"] = res["dram_gbs_from_counters"] / float(measured_peaks().get("hbm_gbs", 6455.6))
     del g, eng
     torch.cuda.empty_cache()
     return res

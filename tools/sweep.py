@@ -29,7 +29,6 @@ print("| T | B | dtype | ms / step | solves/s | iterations / solve | arithmetic 
 print("|---|---|---|---|---|---|---|---|---|")
 for T, B, dt in grid:
     r = bench.sweep_point(default_dubins_config(), dev, a.mode, T, B, dt, steps=3 if B >= 262144 else 5)
-    peak = peak64 if dt == "f64" else peak32
-    fr = f"{r['fp64_tflops_executed']:.1f} TFLOP/s = {r['fp64_tflops_executed'] / peak:.2f}" if "fp64_tflops_executed" in r else "-"
-    dr = f"{r['dram_gbs_from_counters'] / 1e3:.2f} TB/s = {r['dram_gbs_from_counters'] / hbm:.2f}" if "dram_gbs_from_counters" in r else "-"
+    fr = f"{r['pipe_tflops_executed']:.1f} TFLOP/s = {r['pipe_frac_executed']:.2f}" if "pipe_frac_executed" in r else "-"
+    dr = f"{r['dram_gbs_from_counters'] / 1e3:.2f} TB/s = {r['hbm_frac_from_counters']:.2f}" if "dram_gbs_from_counters" in r else "-"
     print(f"| {T} | {B} | {dt} | {r['ms_per_step']:.2f} | {r['value'] / 1e6:.2f} M | {r['iters_per_solve']:.1f} | {fr} | {dr} | {r['nonfinite']} |", flush=True)

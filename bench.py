@@ -709,7 +709,7 @@ def main():
             binds = ("fp64 pipe" if frac_exec >= hbm_frac_act else "hbm") + \
                 f": executed fp64 pipe {frac_exec:.2f} of peak, measured DRAM traffic {hbm_frac_act:.2f} of HBM peak"
         roofline = {"bound": "fp64" if is64 else "fp32",
-                    "kernel": "dtmpc_tube_step launch sequence (per OCP: init + max_iter x [ric, fwd, commit]; then sens; largest: fwd_kernel)",
+                    "kernel": "dtmpc_tube_step launch sequence (per OCP: init + max_iter x [ric_kernel, fwdc_kernel]; then sens_kernel; largest: fwdc_kernel, ~60 % of the step)",
                     "achieved": executed["achieved"] if executed else ach_model, "peak": peak, "unit": "TFLOP/s",
                     "frac": frac_exec if executed else (ach_model / peak if peak > 0 else None),
                     "frac_basis": "executed fp64-pipe warp instructions x 64 flop (ncu counters) / time" if executed else

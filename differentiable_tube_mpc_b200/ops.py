@@ -92,18 +92,20 @@ def _const_tensor(values, dtype, device) -> Tensor:
     return t
 
 
-_default_ws: Dict[int, Workspace] = {}
+_default_ws: Dict[tuple, Workspace] = {}
 
 
 def default_workspace(device) -> Workspace:
-    """The scratch every operator uses when the caller passes no `workspace`: ONE buffer set per device.  Calls on a
-    device are stream-ordered against each other only if they run on the same stream: callers that drive several streams
-    or host threads on one device must give each its own `Workspace` (as `BatchedTubeMPC` does per engine)."""
+    """The scratch every operator uses when the caller passes no `workspace`: one buffer set per (device, current
+    stream), so calls that are not stream-ordered against each other (e.g. an autograd backward on a side stream)
+    never share scratch.  Host threads that enqueue on the SAME stream concurrently must still pass their own
+    `Workspace` (as `BatchedTubeMPC` does per engine)."""
     device = torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    if idx not in _default_ws:
-        _default_ws[idx] = Workspace(torch.device("cuda", idx))
-    return _default_ws[idx]
+    key = (idx, int(torch.cuda.current_stream(idx).cuda_stream))
+    if key not in _default_ws:
+        _default_ws[key] = Workspace(torch.device("cuda", idx))
+    return _default_ws[key]
 
 
 @dataclass

@@ -411,3 +411,16 @@ def test_device_closed_loop_batch():
     bad[3, 0] = float("nan")
     with pytest.raises(FloatingPointError):
         ClosedLoop(cfg, device=DEV, batch=8, x0=bad).run(2)
+
+
+def test_default_workspace_is_per_stream():
+    """calls that are not stream-ordered against each other must not share scratch."""
+    from differentiable_tube_mpc_b200 import ops
+
+    a = ops.default_workspace(DEV)
+    assert ops.default_workspace(DEV) is a
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        b = ops.default_workspace(DEV)
+        assert ops.default_workspace(DEV) is b
+    assert b is not a and ops.default_workspace(DEV) is a

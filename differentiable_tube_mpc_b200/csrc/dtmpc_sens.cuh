@@ -90,8 +90,11 @@ template <typename R> __device__ __forceinline__ void store_grads(R *out, const 
 #ifndef DTMPC_SENS_MAXNREG
 #define DTMPC_SENS_MAXNREG 255
 #endif
+#ifndef DTMPC_SENS_MAXNREG_F32
+#define DTMPC_SENS_MAXNREG_F32 255
+#endif
 template <typename R, int NOBS = -1>
-__global__ void __maxnreg__(DTMPC_SENS_MAXNREG) sens_kernel(const __grid_constant__ SensParams<R> P) {
+__global__ void __maxnreg__(sizeof(R) == 8 ? DTMPC_SENS_MAXNREG : DTMPC_SENS_MAXNREG_F32) sens_kernel(const __grid_constant__ SensParams<R> P) {
     using m = M<R>;
     const long long i = (long long)blockIdx.x * SENS_BLOCK + threadIdx.x;
     if (i >= P.B) return;

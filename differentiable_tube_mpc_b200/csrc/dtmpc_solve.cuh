@@ -199,13 +199,16 @@ __global__ void __launch_bounds__(LS_BLOCK) init_kernel(const __grid_constant__ 
 #ifndef DTMPC_RIC_MAXNREG
 #define DTMPC_RIC_MAXNREG 128
 #endif
+#ifndef DTMPC_RIC_MAXNREG_F32
+#define DTMPC_RIC_MAXNREG_F32 128
+#endif
 #ifndef DTMPC_RIC_BLOCK
 #define DTMPC_RIC_BLOCK 64
 #endif
 constexpr int RIC_BLOCK = DTMPC_RIC_BLOCK;
 
 template <typename R>
-__global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant__ SolveParams<R> P) {
+__global__ void __maxnreg__(sizeof(R) == 8 ? DTMPC_RIC_MAXNREG : DTMPC_RIC_MAXNREG_F32) ric_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     const int n_act = P.ws.counts[P.parity];
     const int j = blockIdx.x * RIC_BLOCK + threadIdx.x;
@@ -380,6 +383,9 @@ __global__ void __maxnreg__(DTMPC_RIC_MAXNREG) ric_kernel(const __grid_constant_
 #ifndef DTMPC_FWD_MAXNREG
 #define DTMPC_FWD_MAXNREG 72
 #endif
+#ifndef DTMPC_FWD_MAXNREG_F32
+#define DTMPC_FWD_MAXNREG_F32 48   // the float instantiation takes 63 uncapped; 48 -> 10 CTAs per SM: step 8.07 -> 7.53 ms (44: 8.2, 40: 8.7)
+#endif
 
 // The per-instance parameters a rollout step needs (12 values) are the same for every candidate warp of the CTA and
 // constant over the sweep: parked in shared memory and re-read each step they cost 12 LDS instead of ~24 registers.
@@ -429,7 +435,7 @@ constexpr int FWDC_MAX_SEG = DTMPC_MAX_ALPHAS;
 #endif
 
 template <typename R, int NOBS = -1, int UR = -1>
-__global__ void __maxnreg__(DTMPC_FWD_MAXNREG) fwdc_kernel(const __grid_constant__ SolveParams<R> P) {
+__global__ void __maxnreg__(sizeof(R) == 8 ? DTMPC_FWD_MAXNREG : DTMPC_FWD_MAXNREG_F32) fwdc_kernel(const __grid_constant__ SolveParams<R> P) {
     using m = M<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *sJ = reinterpret_cast<R *>(smem_raw);                 // [MAX_ALPHAS][32] candidate costs

@@ -666,7 +666,7 @@ def main():
                 r2, _ = bench_nominal(cfg2, dev, torch.float64, NOMINAL_BATCH, 20, 3)
                 extras["cfg2_nominal_B4096"] = r2
                 sweep = []
-                for Tq, Bq, dq in ((20, 65536, "f64"), (100, 65536, "f64"), (200, 32768, "f64"), (50, 65536, "f32")):
+                for Tq, Bq, dq in ((20, 65536, "f64"), (100, 65536, "f64"), (200, 65536, "f64"), (50, 65536, "f32")):
                     sweep.append(sweep_point(default_dubins_config(), dev, args.mode, Tq, Bq, dq, steps=4))
                 extras["cfg4_sweep"] = sweep
                 extras["cfg1_closed_loop_B65536"] = bench_closed_loop(default_dubins_config(), dev, 65536, 10, "paper")

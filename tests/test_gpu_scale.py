@@ -31,10 +31,25 @@ def cu(a):
 
 @pytest.mark.parametrize("mode", ["full"])
 def test_bench_batch_matches_the_oracle(oracle, mode):
+    _batch_vs_oracle(oracle, mode, B_BENCH, bench.T_HORIZON, max_mismatch=0.002, max_illc=0.002)
+
+
+# BASELINE configs[3] (the horizon sweep of bench.py / tools/sweep.py) at its own horizons; the bounds are the measured
+# shares (printed), rounded up
+# measured on B200: T = 20: 9 tie mismatches of 16,384, ill-conditioned 0.16 %; T = 100: 0 / 0.95 %; T = 200: 0 / 5.3 %
+# (a 1e-14 perturbation of x0 grows with the horizon: more instances pass the 1e-10 mark and are compared at 10 x their
+# own measured sensitivity instead of 1e-9)
+@pytest.mark.parametrize("T,B,max_mismatch,max_illc", [(20, 16384, 0.002, 0.003), (100, 4096, 0.002, 0.012),
+                                                       (200, 2048, 0.002, 0.06)])
+def test_sweep_horizons_match_the_oracle(oracle, T, B, max_mismatch, max_illc):
+    _batch_vs_oracle(oracle, "full", B, T, max_mismatch=max_mismatch, max_illc=max_illc)
+
+
+def _batch_vs_oracle(oracle, mode, B, T, max_mismatch, max_illc):
     from differentiable_tube_mpc_b200 import default_dubins_config, ops
 
     cfg = default_dubins_config()
-    B, T = B_BENCH, bench.T_HORIZON
+    cfg["system"]["horizon_N"] = T
     prob, w = bench.make_workload(cfg, mode, 0, B, B)
     env = oracle.env_from_cfg(cfg)
     nom, aux = oracle.ocps_from_cfg(cfg, mode)
@@ -50,9 +65,14 @@ def test_bench_batch_matches_the_oracle(oracle, mode):
     want = oracle.tube_solve_batch(env, nom, aux, x0n, x0a, V0, V0, theta_n=th_n, theta_a=th_a, mode=mode, n_threads=threads)
     pert = oracle.tube_solve_batch(env, nom, aux, x0n * (1 + 1e-14), x0a * (1 + 1e-14), V0, V0, theta_n=th_n,
                                    theta_a=th_a, mode=mode, n_threads=threads)
+    # k = -Q_uu^-1 Q_u is a residual (~0 at the optimum) left by cancellation in Q_u = l_u + B^T V_x, and V_x sums one
+    # term per remaining step: its absolute roundoff grows with the horizon, so does the floor it is compared on
+    k_floor = 1e-3 * max(1.0, T / 50.0)
     cond = np.zeros(B)
-    for k in ("Xn", "Un", "Xa", "Ua", "dXa", "dLa"):
+    for k in ("Xn", "Un", "Xa", "Ua", "dXa", "dLa", "Kn", "Ka"):
         cond = np.maximum(cond, per_instance_rel(pert[k], want[k], floor=1e-6))
+    for k in ("kn", "ka"):
+        cond = np.maximum(cond, per_instance_rel(pert[k], want[k], floor=k_floor))
     del pert
 
     rn, ra, sa, sn = ops.tube_step_batched(prob.system, prob.nominal, prob.auxiliary, cu(x0n), cu(x0a), cu(V0), cu(V0),
@@ -86,13 +106,14 @@ def test_bench_batch_matches_the_oracle(oracle, mode):
     mism = ok & ~same
     illc = ok & (cond > 1e-10)
     unexplained = mism & ~tie & ~(cond > 1e-12)
-    print(f"[scale {mode}] B={B}: decisions identical on {(ok & same).mean():.4%}; mismatches {mism.sum()} "
+    print(f"[scale {mode}] T={T} B={B}: decisions identical on {(ok & same).mean():.4%}; mismatches {mism.sum()} "
           f"(ties {int((mism & tie).sum())}, ill-conditioned {int((mism & ~tie & (cond > 1e-12)).sum())}, "
           f"unexplained {int(unexplained.sum())}); ill-conditioned share {illc.mean():.3%}")
     assert unexplained.sum() == 0, np.nonzero(unexplained)[0][:10]
-    # measured on B200 (round 2): 3 mismatches of 65,536 (0.005 %, all ties), ill-conditioned share 0.021 %
-    assert mism.mean() <= 0.002, f"decision mismatch share {mism.mean():.3%}"
-    assert illc.mean() <= 0.002, f"ill-conditioned share {illc.mean():.3%}"
+    # measured on B200 (round 2) at T = 50, B = 65,536: 3 mismatches (0.005 %, all ties), ill-conditioned share 0.12 %
+    # (0.02 % by states / controls / sensitivities alone; the rest are instances whose feed-forward gain k moves)
+    assert mism.mean() <= max_mismatch, f"decision mismatch share {mism.mean():.3%}"
+    assert illc.mean() <= max_illc, f"ill-conditioned share {illc.mean():.3%}"
 
     # ---- values ------------------------------------------------------------------------------------------------
     def compare(got, key, sel, floor=0.0):
@@ -106,7 +127,7 @@ def test_bench_batch_matches_the_oracle(oracle, mode):
     sel = ok & same
     compare(rn.X, "Xn", sel); compare(rn.V, "Un", sel); compare(ra.X, "Xa", sel); compare(ra.V, "Ua", sel)
     compare(rn.K, "Kn", sel); compare(ra.K, "Ka", sel)
-    compare(rn.k, "kn", sel, floor=1e-3); compare(ra.k, "ka", sel, floor=1e-3)
+    compare(rn.k, "kn", sel, floor=k_floor); compare(ra.k, "ka", sel, floor=k_floor)
     # sensitivities and gradients come out of the same call (evaluated at the product's own optimum)
     well = sel & (cond <= 1e-11)
     compare(sa.delta_X, "dXa", well, floor=1e-6); compare(sa.delta_V, "dVa", well, floor=1e-6)

@@ -24,15 +24,18 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     st = eng.step(x0n, x0a, V0, V0, thn, tha, full=(a.mode == "full")); torch.cuda.synchronize()
 evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
 short = lambda e: e.name.split("<")[0].replace("void dtmpc::", "").replace("void ", "")
-rows = {"ric_kernel": [], "fwd_kernel": [], "commit_kernel": []}
+rows = {"ric_kernel": [], "fwdc_kernel": []}
 for e in evs:
     if short(e) in rows: rows[short(e)].append(e.time_range.end - e.time_range.start)
-for name, res, off in (("nominal", st.nominal, 0), ("auxiliary", st.auxiliary, 1)):
-    it = res.iters.cpu().numpy(); n_it = len(rows["ric_kernel"]) // 2
+# one chunk per call (DTMPC_CHUNKS=1): the launches come in the order nominal iterations, auxiliary iterations
+n_nom, n_aux = prob.nominal.ilqr.max_iter, prob.auxiliary.ilqr.max_iter
+assert len(rows["ric_kernel"]) == n_nom + n_aux, "run with DTMPC_CHUNKS=1"
+for name, res, first, n_it in (("nominal", st.nominal, 0, n_nom), ("auxiliary", st.auxiliary, n_nom, n_aux)):
+    it = res.iters.cpu().numpy()
     print(f"== {name}: mean iters {it.mean():.2f}, max {it.max()}")
-    print(" it   active   ric_us   fwd_us   sel_us   ric ns/inst  fwd ns/inst  sel ns/inst")
+    print(" it   active   ric_us  fwdc_us   ric ns/inst  fwdc ns/inst")
     for j in range(n_it):
         act = int((it > j).sum()) if j > 0 else a.batch   # an instance runs iteration j iff it did not stop before it
-        r, f, s = (rows[k][off * n_it + j] for k in ("ric_kernel", "fwd_kernel", "commit_kernel"))
+        r, f = (rows[k][first + j] for k in ("ric_kernel", "fwdc_kernel"))
         m = max(act, 1)
-        print(f"{j:3d} {act:8d} {r:8.1f} {f:8.1f} {s:8.1f}   {1e3 * r / m:9.2f}  {1e3 * f / m:9.2f}  {1e3 * s / m:9.2f}")
+        print(f"{j:3d} {act:8d} {r:8.1f} {f:8.1f}   {1e3 * r / m:9.2f}  {1e3 * f / m:9.2f}")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Static opcode mix of a kernel's SASS (whole function or its hottest backward-branch loop).
 
-    python tools/sass_loop.py [--lib path.so] --kernel fwd_kernelIdLi1ELi5ELi1 [--loop]
+    python tools/sass_loop.py [--lib path.so] --kernel fwdc_kernelIdLi5ELi0E [--loop]
 
 --loop restricts the count to the largest loop (the span of the longest backward branch).  A static count is a proxy
 only (slow paths that never execute are included); the dynamic mix comes from ncu (profiles/).

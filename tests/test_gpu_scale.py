@@ -209,3 +209,50 @@ def test_nominal_config2_batch_matches_the_oracle(oracle):
     # (worst 1.3e-10); the other 534 each PROVED a roundoff tie or an oracle answer that moves under a 1e-14 perturbation
     # of x0 (asserted above, instance by instance): trajectories that skirt an obstacle have jacobian entries ~1e8
     assert n_tame >= 0.7 * B and n_same >= 0.8 * n_tame and worst < 1e-9
+
+
+def test_million_instance_batch_is_indexed_in_64_bits():
+    """BASELINE configs[3] at its largest batch (B = 1,048,576) and T = 100: the sensitivity scratch alone is 4.1e9
+    elements, past 2^31, and every per-instance offset of the API tensors is past 2^31 BYTES from a few thousand
+    instances on.  Size-independent properties on the whole batch, and slices from the far end and from the middle solved
+    again on their own must give bitwise the same answers (solutions, sensitivities, gradients)."""
+    from differentiable_tube_mpc_b200 import default_dubins_config, ops
+
+    if torch.cuda.mem_get_info()[0] < 130e9:
+        pytest.skip("needs ~110 GB of free device memory")
+    cfg = default_dubins_config()
+    B, T = 1 << 20, 100
+    cfg["system"]["horizon_N"] = T
+    prob, w = bench.make_workload(cfg, "full", 0, B, B)
+    th_n, th_a = cu(w["th_n"]), cu(w["th_a"])
+    z2 = torch.zeros(B, 2, dtype=torch.float64, device=DEV)
+    x0n = torch.cat([cu(w["xb"]), torch.zeros(B, 1, dtype=torch.float64, device=DEV)], 1)
+    x0a = torch.cat([cu(w["x"]), torch.zeros(B, 1, dtype=torch.float64, device=DEV)], 1)
+    x0n[:, 3] = ops.primitives_batched(prob.system, prob.nominal, x0n, z2, th_n)["b0"]
+    x0a[:, 3] = ops.primitives_batched(prob.system, prob.auxiliary, x0a, z2, th_a)["b0"]
+    V0 = torch.zeros(B, T, 2, dtype=torch.float64, device=DEV)
+    from differentiable_tube_mpc_b200 import _lib
+    assert _lib.load().dtmpc_sens_workspace_bytes(T, B, 8) // 8 > 2 ** 31
+    ws = ops.Workspace(DEV)
+    rn, ra, sa, sn = ops.tube_step_batched(prob.system, prob.nominal, prob.auxiliary, x0n, x0a, V0, V0, th_n, th_a,
+                                           full=True, workspace=ws)
+    torch.cuda.synchronize()
+    ok = rn.status == 0
+    assert float(ok.float().mean()) > 0.999
+    lo, hi = prob.system.ctrl.bounds()
+    for r in (rn, ra):
+        assert bool((r.V >= cu(lo)).all()) and bool((r.V <= cu(hi)).all())
+        assert bool((r.iters >= 2).all())
+    assert bool(torch.isfinite(sa.g_theta[ok]).all()) and bool(torch.isfinite(sn.g_theta[ok]).all())
+    # the far end, the middle and the first tile group on their own (fresh workspace): bitwise the same
+    n = 4096
+    for start in (B - n, B // 2 - n // 2, 0, B - 33):
+        sl = slice(start, min(B, start + n))
+        pn, pa, qa, qn = ops.tube_step_batched(prob.system, prob.nominal, prob.auxiliary, x0n[sl], x0a[sl], V0[sl], V0[sl],
+                                               th_n[sl], th_a[sl], full=True, workspace=ops.Workspace(DEV))
+        for got, want in ((pn.X, rn.X), (pn.V, rn.V), (pa.X, ra.X), (pa.V, ra.V), (pa.iters, ra.iters), (pn.status, rn.status),
+                          (qa.delta_X, sa.delta_X), (qa.delta_lambda, sa.delta_lambda), (qa.g_theta, sa.g_theta),
+                          (qn.delta_V, sn.delta_V), (qn.g_theta, sn.g_theta), (qa.loss, sa.loss)):
+            assert torch.equal(got, want[sl]), start
+        # the returned trajectory is the rollout of the returned controls, bit for bit
+        assert torch.equal(ops.rollout_batched(prob.system, prob.auxiliary, x0a[sl], ra.V[sl], th_a[sl]), ra.X[sl])
